@@ -14,6 +14,7 @@
 #ifndef STB200_H_
 #define STB200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -44,12 +45,78 @@ typedef struct stb_ctx stb_ctx;
 /* Thread-local message for the last failing call on this thread. */
 STB_API const char* stb_last_error(void);
 
+/* ------------------------------------------------------------------ context (replaces ST:324-333)
+ * conv_w[i] / conv_b[i]: DEVICE fp32 pointers to the 13 conv weights (OIHW) and biases of vgg19().features[:30] in
+ * layer order.  The context packs them once into its own bf16 tensor-core layouts (the only memory it owns). */
+STB_API int stb_ctx_create(int device, int pooling, const float* const* conv_w, const float* const* conv_b,
+                           void* stream, stb_ctx** out);
+STB_API void stb_ctx_destroy(stb_ctx* ctx);
+
+/* ------------------------------------------------------------------ workspace (caller/torch owns all memory;
+ * mirrors the reference's per-scale allocations, ST:413-414, 469-470).  Bytes needed to run any entry point on
+ * an H x W image; bind a 1 KiB-aligned device block of at least the maximum over the sizes that will be used.
+ * Rebinding invalidates the targets. */
+STB_API int stb_workspace_bytes(stb_ctx* ctx, int H, int W, size_t* bytes);
+STB_API int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------ target extraction (no-grad VGG forward)
+ * stb_style_stats      = self.model(style, layers=style_layers) + StyleLossW2.get_target   (ST:440-443, 163-168)
+ *                        mean_out[l]: [C_l] fp32, srm_out[l]: [C_l,C_l] fp32, l over taps 1,6,11,20,29
+ * stb_content_features = self.model(content, layers=[22])[22]                               (ST:425)
+ *                        target_out: bf16 NHWC [H/8][W/8][512]
+ * `img` is a device fp32 NCHW [1,3,H,W] tensor with values in [0,1]; H,W >= 16 (ST:61-69, 82-83). */
+STB_API int stb_style_stats(stb_ctx* ctx, const float* img, int H, int W, float* const* mean_out,
+                            float* const* srm_out, void* stream);
+STB_API int stb_content_features(stb_ctx* ctx, const float* img, int H, int W, void* target_out_bf16, void* stream);
+
+/* ------------------------------------------------------------------ per-scale loss state (ST:426-455)
+ * mean_t/srm_t: the style-weight-blended target moments (ST:443-450); the library forms cov = srm - mean mean^T
+ * + eps I and cov_sqrt = sqrtm_ns(cov, 12) (ST:152-160).  style_w: the five layer weights (ST:320-322). */
+STB_API int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16, float content_weight,
+                            const float* const* mean_t, const float* const* srm_t, const float* style_w,
+                            float tv_weight, float eps, void* stream);
+
+/* ------------------------------------------------------------------ THE HOT PATH: one iteration of ST:480-486
+ * forward + losses + backward + Adam(lr, betas, eps; bias correction with `step` = 1-based count carried across
+ * scales, ST:287-295/461-462) + clamp_(0,1) + EMA value update, all stream-ordered with no host sync.
+ * loss_out_host8 (pinned host, optional) receives asynchronously {loss, content, style1..5, tv} of the
+ * PRE-update image (what `opt.step(closure)` returns, ST:481). */
+STB_API int stb_iterate(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step,
+                        float lr, float beta1, float beta2, float adam_eps, float ema_decay, float* loss_out_host8,
+                        void* stream);
+/* closure-only variant (apply_update = 0): loss and d loss/d image (grad_out fp32 NCHW), e.g. for an L-BFGS host. */
+STB_API int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step,
+                           float lr, float beta1, float beta2, float adam_eps, float ema_decay, int apply_update,
+                           float* grad_out, float* loss_out_host8, void* stream);
+
+/* ------------------------------------------------------------------ measurement (bench.py roofline leg)
+ * CUDA-event timing per kernel class on the launching stream; classes in order: conv0_fwd_tv, conv_fwd, pool_fwd,
+ * gram, sse, w2, conv_bwd, pool_bwd, conv0_bwd_adam, finalize (STB_PROF_CLASSES entries). */
+#define STB_PROF_CLASSES 10
+STB_API int stb_profile_enable(stb_ctx* ctx, int enable);
+STB_API int stb_profile_read(stb_ctx* ctx, float* ms_out, int* count_out, int n_classes);
+
 /* ------------------------------------------------------------------ kernel test hooks (used by tests/ only) */
+STB_API int stb_debug_activation(stb_ctx* ctx, int H, int W, int conv_index, void* out_bf16, size_t out_bytes,
+                                 void* stream);
 STB_API int stb_pack_weights(const float* w_oihw, void* out_bf16, int Cout, int Cin, int bwd, void* stream);
 STB_API int stb_test_pixel_gemm(int H, int W, int Cin, int Cout, int C2, int mode, const void* A, const void* Bw,
                                 const void* A2, int a2_row0, int a2_rows, const void* B2, void* out,
                                 const float* bias, const void* mask_src, const void* ctarget, float cscale,
                                 int row_lo, int row_hi, void* stream);
+STB_API int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void* out_bf16, int H, int W,
+                               float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream);
+STB_API int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
+                               void* stream);
+STB_API int stb_test_pool(int pooling, int backward, const void* in_or_gout, const void* y, void* out, int H, int W,
+                          int C, void* stream);
+STB_API int stb_test_gram(const void* F_bf16, long P, int C, float* partials_ws, size_t partials_floats,
+                          float* S_raw, float* sums, void* stream);
+STB_API size_t stb_test_gram_partials_floats(long P, int C);
+STB_API int stb_test_w2(const float* mean_t, const float* srm_t, const float* S_raw, const float* sums, int C,
+                        float npix, float weight, void* ws, size_t ws_bytes, float* loss_out, float* gs_out,
+                        float* gmu_out, float* csqrt_out, void* stream);
+STB_API size_t stb_test_w2_workspace_bytes(void);
 
 #ifdef __cplusplus
 }

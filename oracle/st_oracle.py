@@ -409,7 +409,7 @@ def _interp(x, size, mode):
 
 def to_tensor(pil_image):
     arr = np.asarray(pil_image.convert('RGB'), dtype=np.uint8)
-    return torch.from_numpy(arr.copy()).permute(2, 0, 1).float().div(255)[None]
+    return torch.from_numpy(arr.copy()).permute(2, 0, 1).float().div(255)[None].contiguous()
 
 
 def make_targets(content_pil, style_pils, style_weights, scale, weights, pooling, content_weight, tv_weight,

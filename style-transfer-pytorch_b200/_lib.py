@@ -1,0 +1,97 @@
+"""ctypes binding of libstb200.so (include/stb200.h).  No fallback: a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / 'libstb200.so'
+
+STB_ERR_INVALID = -1
+POOLING = {'max': 0, 'average': 1, 'l2': 2}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, i, f, sz, i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+    pp = C.POINTER(C.c_void_p)
+    lib.stb_last_error.restype = C.c_char_p
+    lib.stb_last_error.argtypes = []
+    sigs = {
+        'stb_ctx_create': [i, i, pp, pp, vp, pp],
+        'stb_workspace_bytes': [vp, i, i, C.POINTER(sz)],
+        'stb_bind_workspace': [vp, vp, sz, vp],
+        'stb_style_stats': [vp, vp, i, i, pp, pp, vp],
+        'stb_content_features': [vp, vp, i, i, vp, vp],
+        'stb_set_targets': [vp, i, i, vp, f, pp, pp, C.POINTER(f), f, f, vp],
+        'stb_iterate': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, vp, vp],
+        'stb_iterate_ex': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, i, vp, vp, vp],
+        'stb_profile_enable': [vp, i],
+        'stb_profile_read': [vp, C.POINTER(f), C.POINTER(i), i],
+        'stb_debug_activation': [vp, i, i, i, vp, sz, vp],
+        'stb_pack_weights': [vp, vp, i, i, i, vp],
+        'stb_test_pixel_gemm': [i, i, i, i, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, f, i, i, vp],
+        'stb_test_conv0_fwd': [vp, vp, vp, vp, i, i, f, vp, vp, C.POINTER(i), vp],
+        'stb_test_conv0_bwd': [vp, vp, vp, vp, i, i, vp],
+        'stb_test_pool': [i, i, vp, vp, vp, i, i, i, vp],
+        'stb_test_gram': [vp, C.c_long, i, vp, sz, vp, vp, vp],
+        'stb_test_w2': [vp, vp, vp, vp, i, f, f, vp, sz, vp, vp, vp, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.stb_ctx_destroy.argtypes = [vp]
+    lib.stb_ctx_destroy.restype = None
+    lib.stb_test_gram_partials_floats.argtypes = [C.c_long, i]
+    lib.stb_test_gram_partials_floats.restype = sz
+    lib.stb_test_w2_workspace_bytes.argtypes = []
+    lib.stb_test_w2_workspace_bytes.restype = sz
+
+
+EXPORTS = [
+    'stb_last_error', 'stb_ctx_create', 'stb_ctx_destroy', 'stb_workspace_bytes', 'stb_bind_workspace',
+    'stb_style_stats', 'stb_content_features', 'stb_set_targets', 'stb_iterate', 'stb_iterate_ex',
+    'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation', 'stb_pack_weights', 'stb_test_pixel_gemm', 'stb_test_conv0_fwd', 'stb_test_conv0_bwd',
+    'stb_test_pool', 'stb_test_gram', 'stb_test_gram_partials_floats', 'stb_test_w2', 'stb_test_w2_workspace_bytes',
+]
+
+
+def load():
+    """Load libstb200.so (built in-tree by build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise NativeError(f'{LIB_PATH} is missing: build it with `python __graft_entry__.py` '
+                              '(there is no CPU or PyTorch fallback for the hot path)')
+        lib = C.CDLL(str(LIB_PATH))
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().stb_last_error().decode(errors='replace')
+        if rc == STB_ERR_INVALID:
+            raise ValueError(msg)
+        raise NativeError(f'libstb200 error {rc}: {msg}')
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return C.cast(arr, C.POINTER(C.c_void_p)), arr
+
+
+def cur_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

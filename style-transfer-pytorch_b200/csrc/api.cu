@@ -1,0 +1,525 @@
+// C-ABI of the B200-native stylize() hot path (see include/stb200.h).  The context owns an explicit, static
+// forward/backward schedule for torchvision vgg19().features[:30] -- no autograd on the path:
+//   forward   ST:78-90     conv0 (+TV) -> 12 x tcgen05 conv/bias/ReLU, 4 pools, taps 1,6,11,20,22,29
+//   losses    ST:119-126, 149-181, 184-195, 198-234  content MSE, 5 x W2 style (Gram on tcgen05, sqrtm in fp32), TV
+//   backward  ST:475       tap-gradient GEMMs folded into the dgrad chain, pool backward, conv0 dgrad
+//   update    ST:481-486   Adam + clamp + EMA fused into the last kernel
+#include <cmath>
+#include <cstring>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+using namespace stb;
+
+namespace {
+
+constexpr int NCONV = STB_NUM_CONVS;
+const int kCin[NCONV] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512};
+const int kCout[NCONV] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512};
+const bool kPoolAfter[NCONV] = {false, true, false, true, false, false, false, true, false, false, false, true, false};
+const int kStyleConv[5] = {0, 2, 4, 8, 12};  // convs whose ReLU output is style tap 1, 6, 11, 20, 29 (ST:317)
+constexpr int kContentConv = 9;              // relu4_2 = layer 22 (ST:316)
+const int kStyleC[5] = {64, 128, 256, 512, 512};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {
+  int H = 0, W = 0;
+  int h[NCONV], w[NCONV];      // spatial size of conv i's input == output
+  size_t act_off[NCONV];       // post-ReLU output of conv i (bf16 NHWC)
+  size_t pool_off[4];          // pooled copies
+  size_t g_off[2];             // gradient ping-pong
+  size_t gtv_off, tvp_off, ssep_off, gramp_off, stats_off, loss_off, ctarget_off;
+  size_t stats_layer_off[5];   // in floats, inside the stats block: S_raw then sums per layer
+  size_t total = 0;
+  int n_tv_partials = 0, n_sse_partials = 0;
+};
+
+}  // namespace
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
+enum ProfClass { PC_CONV0_FWD = 0, PC_CONV_FWD, PC_POOL_FWD, PC_GRAM, PC_SSE, PC_W2, PC_CONV_BWD, PC_POOL_BWD,
+                 PC_CONV0_BWD_ADAM, PC_FINALIZE, PC_COUNT };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  struct Span { int cls; int e0, e1; };
+  std::vector<Span> spans;
+  int used = 0;
+  int get_event() {
+    if (used == (int)pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return used++;
+  }
+  void begin(int cls, cudaStream_t s) {
+    if (!on) return;
+    Span sp{cls, get_event(), -1};
+    cudaEventRecord(pool[sp.e0], s);
+    spans.push_back(sp);
+  }
+  void end(cudaStream_t s) {
+    if (!on) return;
+    spans.back().e1 = get_event();
+    cudaEventRecord(pool[spans.back().e1], s);
+  }
+};
+
+struct stb_ctx {
+  Prof prof;
+  int device = 0;
+  int pooling = STB_POOL_MAX;
+  float* w0 = nullptr;  // conv0 fp32 OIHW (borrowed copy)
+  float* bias[NCONV] = {};
+  bf16* wf[NCONV] = {};  // packed forward weights  [9][Cout][Cin]
+  bf16* wb[NCONV] = {};  // packed dgrad weights    [9][Cin][Cout]
+  void* owned = nullptr; // one cudaMalloc block holding all of the above
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t w2_bytes = 0;
+  W2Engine w2;
+  bool w2_ready = false;
+  // per-scale loss state
+  bool targets_set = false;
+  int tH = 0, tW = 0;
+  float content_weight = 0.f, tv_weight = 0.f;
+  float style_w[5] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+
+namespace {
+
+void make_plan(const stb_ctx* ctx, int H, int W, Plan* pl) {
+  pl->H = H; pl->W = W;
+  int h = H, w = W;
+  size_t off = align_up(ctx->w2_bytes, 1024);
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  int np = 0;
+  size_t gmax = 0;
+  for (int i = 0; i < NCONV; ++i) {
+    pl->h[i] = h; pl->w[i] = w;
+    pl->act_off[i] = take((size_t)h * w * kCout[i] * 2);
+    gmax = std::max(gmax, (size_t)h * w * kCout[i] * 2);
+    if (kPoolAfter[i]) {
+      h /= 2; w /= 2;
+      pl->pool_off[np++] = take((size_t)std::max(h, 1) * std::max(w, 1) * kCout[i] * 2);
+    }
+  }
+  pl->g_off[0] = take(gmax);
+  pl->g_off[1] = take(gmax);
+  pl->gtv_off = take((size_t)3 * H * W * 4);
+  pl->n_tv_partials = ((W + 63) / 64) * H;
+  pl->tvp_off = take((size_t)pl->n_tv_partials * 4);
+  pl->ssep_off = take(1024 * 4);
+  size_t gp = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int ci = kStyleConv[l];
+    gp = std::max(gp, gram_partials_floats((long)pl->h[ci] * pl->w[ci], kStyleC[l]));
+  }
+  pl->gramp_off = take(gp * 4);
+  size_t sf = 0;
+  for (int l = 0; l < 5; ++l) { pl->stats_layer_off[l] = sf; sf += (size_t)kStyleC[l] * kStyleC[l] + kStyleC[l]; }
+  pl->stats_off = take(sf * 4);
+  pl->loss_off = take(64 * 4);
+  pl->ctarget_off = take((size_t)pl->h[kContentConv] * pl->w[kContentConv] * 512 * 2);
+  pl->total = off;
+}
+
+int check_size(int H, int W, int last_conv) {
+  int min_size = 1;
+  for (int i = 0; i < last_conv; ++i)
+    if (kPoolAfter[i]) min_size *= 2;
+  STB_CHECK(H >= min_size && W >= min_size && H > 0 && W > 0, STB_ERR_INVALID,
+            "Input is %dx%d but must be at least %dx%d", H, W, min_size, min_size);  // ST:82-83
+  return STB_OK;
+}
+
+int ensure_ws(const stb_ctx* ctx, const Plan& pl) {
+  STB_CHECK(ctx->ws != nullptr, STB_ERR_WORKSPACE, "no workspace bound (call stb_bind_workspace)");
+  STB_CHECK(pl.total <= ctx->ws_bytes, STB_ERR_WORKSPACE, "workspace too small for %dx%d: need %zu bytes, have %zu",
+            pl.H, pl.W, pl.total, ctx->ws_bytes);
+  return STB_OK;
+}
+
+template <typename T>
+T* at(const stb_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->ws + off); }
+
+// forward through conv `last_conv` (inclusive); do_tv also produces the TV gradient / loss partials
+int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool do_tv, cudaStream_t s) {
+  int ntv = 0;
+  ctx->prof.begin(PC_CONV0_FWD, s);
+  STB_TRY(launch_conv0_fwd(img, ctx->w0, ctx->bias[0], at<bf16>(ctx, pl.act_off[0]), pl.H, pl.W, ctx->tv_weight,
+                           do_tv ? at<float>(ctx, pl.gtv_off) : nullptr, at<float>(ctx, pl.tvp_off), &ntv, s));
+  ctx->prof.end(s);
+  int np = 0;
+  const bf16* cur = at<bf16>(ctx, pl.act_off[0]);
+  for (int i = 1; i <= last_conv; ++i) {
+    if (kPoolAfter[i - 1]) {
+      bf16* po = at<bf16>(ctx, pl.pool_off[np++]);
+      ctx->prof.begin(PC_POOL_FWD, s);
+      STB_TRY(launch_pool_fwd(ctx->pooling, cur, po, pl.h[i - 1], pl.w[i - 1], kCout[i - 1], s));
+      ctx->prof.end(s);
+      cur = po;
+    }
+    PixelGemmArgs a;
+    a.H = pl.h[i]; a.W = pl.w[i]; a.Cin = kCin[i]; a.Cout = kCout[i]; a.mode = 0;
+    a.A = cur; a.Bw = ctx->wf[i]; a.out = at<bf16>(ctx, pl.act_off[i]); a.bias = ctx->bias[i];
+    ctx->prof.begin(PC_CONV_FWD, s);
+    STB_TRY(launch_pixel_gemm(a, s));
+    ctx->prof.end(s);
+    cur = a.out;
+  }
+  return STB_OK;
+}
+
+int style_grams(stb_ctx* ctx, const Plan& pl, cudaStream_t s) {
+  float* stats = at<float>(ctx, pl.stats_off);
+  ctx->prof.begin(PC_GRAM, s);
+  for (int l = 0; l < 5; ++l) {
+    const int ci = kStyleConv[l];
+    const int C = kStyleC[l];
+    float* S = stats + pl.stats_layer_off[l];
+    STB_TRY(launch_gram(at<bf16>(ctx, pl.act_off[ci]), (long)pl.h[ci] * pl.w[ci], C, at<float>(ctx, pl.gramp_off), S,
+                        S + (size_t)C * C, s));
+  }
+  ctx->prof.end(s);
+  return STB_OK;
+}
+
+__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long n, float scale) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = in[i] * scale;
+}
+
+// loss = cw * sse / numel + sum_l style_l + tvw * tv   (python sum, left to right, ST:208/455)
+__global__ void finalize_loss_kernel(const float* __restrict__ sse_p, int n_sse, float content_scale,
+                                     const float* __restrict__ style_terms, const float* __restrict__ tv_p, int n_tv,
+                                     float tv_weight, float* __restrict__ out) {
+  __shared__ float s_red[32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < n_sse; i += blockDim.x) a += sse_p[i];
+  for (int i = threadIdx.x; i < n_tv; i += blockDim.x) b += tv_p[i];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  float ta = 0.f;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) ta += s_red[i];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tb = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tb += s_red[i];
+    const float content = ta * content_scale;
+    const float tv = tb * tv_weight;
+    float loss = content;
+    for (int l = 0; l < 5; ++l) loss += style_terms[l];
+    loss += tv;
+    out[0] = loss;
+    out[1] = content;
+    for (int l = 0; l < 5; ++l) out[2 + l] = style_terms[l];
+    out[7] = tv;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int stb_ctx_create(int device, int pooling, const float* const* conv_w, const float* const* conv_b, void* stream,
+                   stb_ctx** out) {
+  STB_CHECK(out != nullptr && conv_w != nullptr && conv_b != nullptr, STB_ERR_INVALID, "null argument");
+  STB_CHECK(pooling >= 0 && pooling <= 2, STB_ERR_INVALID, "pooling must be STB_POOL_MAX/AVERAGE/L2");
+  STB_CUDA_CHECK(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  stb_ctx* ctx = new stb_ctx();
+  ctx->device = device;
+  ctx->pooling = pooling;
+  size_t bytes = 0;
+  for (int i = 0; i < NCONV; ++i) {
+    bytes += align_up((size_t)kCout[i] * 4, 256);
+    if (i == 0) bytes += align_up((size_t)64 * 27 * 4, 256);
+    else bytes += 2 * align_up((size_t)9 * kCout[i] * kCin[i] * 2, 256);
+  }
+  cudaError_t e = cudaMalloc(&ctx->owned, bytes);
+  if (e != cudaSuccess) { delete ctx; return set_error(STB_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  uint8_t* p = static_cast<uint8_t*>(ctx->owned);
+  auto take = [&](size_t b) { void* r = p; p += align_up(b, 256); return r; };
+  for (int i = 0; i < NCONV; ++i) {
+    ctx->bias[i] = (float*)take((size_t)kCout[i] * 4);
+    STB_CUDA_CHECK(cudaMemcpyAsync(ctx->bias[i], conv_b[i], (size_t)kCout[i] * 4, cudaMemcpyDeviceToDevice, s));
+    if (i == 0) {
+      ctx->w0 = (float*)take(64 * 27 * 4);
+      STB_CUDA_CHECK(cudaMemcpyAsync(ctx->w0, conv_w[0], 64 * 27 * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      ctx->wf[i] = (bf16*)take((size_t)9 * kCout[i] * kCin[i] * 2);
+      ctx->wb[i] = (bf16*)take((size_t)9 * kCout[i] * kCin[i] * 2);
+      STB_TRY(pack_weights_fwd(conv_w[i], ctx->wf[i], kCout[i], kCin[i], s));
+      STB_TRY(pack_weights_bwd(conv_w[i], ctx->wb[i], kCout[i], kCin[i], s));
+    }
+  }
+  ctx->w2_bytes = W2Engine::workspace_bytes();
+  STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  *out = ctx;
+  return STB_OK;
+}
+
+void stb_ctx_destroy(stb_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->owned) cudaFree(ctx->owned);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  delete ctx;
+}
+
+int stb_workspace_bytes(stb_ctx* ctx, int H, int W, size_t* bytes) {
+  STB_CHECK(ctx && bytes, STB_ERR_INVALID, "null argument");
+  STB_TRY(check_size(H, W, 0));
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  *bytes = pl.total;
+  return STB_OK;
+}
+
+int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream) {
+  STB_CHECK(ctx != nullptr, STB_ERR_INVALID, "null ctx");
+  STB_CHECK(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 1023) == 0, STB_ERR_INVALID,
+            "workspace must be a 1 KiB aligned device pointer");
+  STB_CHECK(bytes >= ctx->w2_bytes + 4096, STB_ERR_WORKSPACE, "workspace smaller than the fixed W2 block");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  ctx->ws = static_cast<uint8_t*>(ptr);
+  ctx->ws_bytes = bytes;
+  ctx->targets_set = false;
+  STB_TRY(ctx->w2.init(ctx->ws, ctx->w2_bytes, kStyleC));
+  ctx->w2_ready = true;
+  return STB_OK;
+}
+
+int stb_style_stats(stb_ctx* ctx, const float* img, int H, int W, float* const* mean_out, float* const* srm_out,
+                    void* stream) {
+  STB_CHECK(ctx && img && mean_out && srm_out, STB_ERR_INVALID, "null argument");
+  STB_TRY(check_size(H, W, NCONV - 1));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  STB_TRY(forward(ctx, pl, img, NCONV - 1, false, s));
+  STB_TRY(style_grams(ctx, pl, s));
+  const float* stats = at<float>(ctx, pl.stats_off);
+  for (int l = 0; l < 5; ++l) {
+    const int C = kStyleC[l];
+    const int ci = kStyleConv[l];
+    const float inv = 1.f / ((float)pl.h[ci] * (float)pl.w[ci]);
+    const float* S = stats + pl.stats_layer_off[l];
+    scale_copy_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(S, srm_out[l], (long)C * C, inv);
+    scale_copy_kernel<<<1, 256, 0, s>>>(S + (size_t)C * C, mean_out[l], C, inv);
+  }
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int stb_content_features(stb_ctx* ctx, const float* img, int H, int W, void* target_out_bf16, void* stream) {
+  STB_CHECK(ctx && img && target_out_bf16, STB_ERR_INVALID, "null argument");
+  STB_TRY(check_size(H, W, kContentConv));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  STB_TRY(forward(ctx, pl, img, kContentConv, false, s));
+  const size_t bytes = (size_t)pl.h[kContentConv] * pl.w[kContentConv] * 512 * 2;
+  STB_CUDA_CHECK(cudaMemcpyAsync(target_out_bf16, at<bf16>(ctx, pl.act_off[kContentConv]), bytes,
+                                 cudaMemcpyDeviceToDevice, s));
+  return STB_OK;
+}
+
+int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16, float content_weight,
+                    const float* const* mean_t, const float* const* srm_t, const float* style_w, float tv_weight,
+                    float eps, void* stream) {
+  STB_CHECK(ctx && content_target_bf16 && mean_t && srm_t && style_w, STB_ERR_INVALID, "null argument");
+  STB_TRY(check_size(H, W, NCONV - 1));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  STB_CHECK(ctx->w2_ready, STB_ERR_STATE, "workspace not bound");
+  const size_t cbytes = (size_t)pl.h[kContentConv] * pl.w[kContentConv] * 512 * 2;
+  STB_CUDA_CHECK(cudaMemcpyAsync(at<bf16>(ctx, pl.ctarget_off), content_target_bf16, cbytes, cudaMemcpyDeviceToDevice, s));
+  float* stats = at<float>(ctx, pl.stats_off);
+  for (int l = 0; l < 5; ++l) {
+    W2Layer& L = ctx->w2.host_layers[l];
+    const int C = kStyleC[l];
+    const int ci = kStyleConv[l];
+    L.eps = eps;
+    L.weight = style_w[l];
+    L.npix = (float)pl.h[ci] * (float)pl.w[ci];
+    L.S_raw = stats + pl.stats_layer_off[l];
+    L.sums = L.S_raw + (size_t)C * C;
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.mean_t, mean_t[l], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.srm_t, srm_t[l], (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+    ctx->style_w[l] = style_w[l];
+  }
+  STB_TRY(ctx->w2.upload_layers(s));
+  STB_TRY(ctx->w2.build_targets(s));
+  ctx->content_weight = content_weight;
+  ctx->tv_weight = tv_weight;
+  ctx->tH = H; ctx->tW = W;
+  ctx->targets_set = true;
+  return STB_OK;
+}
+
+// One pass of ST:480-486.  apply_update = 0 evaluates loss / gradient only (test hook, L-BFGS closure).
+int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
+                   float beta1, float beta2, float adam_eps, float ema_decay, int apply_update, float* grad_out,
+                   float* loss_out_host8, void* stream) {
+  STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
+  STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate");
+  if (apply_update) STB_CHECK(exp_avg && exp_avg_sq && ema && step >= 1, STB_ERR_INVALID, "bad optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int H = ctx->tH, W = ctx->tW;
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+
+  // ---- forward + statistics
+  STB_TRY(forward(ctx, pl, img, NCONV - 1, true, s));
+  STB_TRY(style_grams(ctx, pl, s));
+  const long n22 = (long)pl.h[kContentConv] * pl.w[kContentConv] * 512;
+  int n_sse = 0;
+  ctx->prof.begin(PC_SSE, s);
+  STB_TRY(launch_sse(at<bf16>(ctx, pl.act_off[kContentConv]), at<bf16>(ctx, pl.ctarget_off), n22,
+                     at<float>(ctx, pl.ssep_off), &n_sse, s));
+  ctx->prof.end(s);
+  float* loss_dev = at<float>(ctx, pl.loss_off);
+  ctx->prof.begin(PC_W2, s);
+  STB_TRY(ctx->w2.forward_backward(loss_dev + 16, s));
+  ctx->prof.end(s);
+
+  // ---- backward
+  bf16* g[2] = {at<bf16>(ctx, pl.g_off[0]), at<bf16>(ctx, pl.g_off[1])};
+  int cur = 0;
+  {  // tap 29: d loss / d conv12 pre-activation = mask * (F Gs / N + gmu / N)
+    const W2Layer& L = ctx->w2.host_layers[4];
+    PixelGemmArgs a;
+    a.H = pl.h[12]; a.W = pl.w[12]; a.Cin = 0; a.Cout = 512; a.C2 = 512; a.mode = 1;
+    a.A2 = at<bf16>(ctx, pl.act_off[12]); a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
+    a.mask_src = at<bf16>(ctx, pl.act_off[12]); a.out = g[cur];
+    ctx->prof.begin(PC_CONV_BWD, s);
+    STB_TRY(launch_pixel_gemm(a, s));
+    ctx->prof.end(s);
+  }
+  int np = 3;
+  for (int i = NCONV - 1; i >= 1; --i) {
+    // g[cur] = gradient w.r.t. conv i pre-activation, [h_i][w_i][Cout_i]; produce gradient for conv i-1
+    PixelGemmArgs a;
+    a.H = pl.h[i]; a.W = pl.w[i]; a.Cin = kCout[i]; a.Cout = kCin[i];
+    a.A = g[cur]; a.Bw = ctx->wb[i]; a.out = g[cur ^ 1];
+    if (kPoolAfter[i - 1]) {
+      a.mode = 2;
+      ctx->prof.begin(PC_CONV_BWD, s);
+      STB_TRY(launch_pixel_gemm(a, s));
+      ctx->prof.end(s);
+      cur ^= 1;
+      ctx->prof.begin(PC_POOL_BWD, s);
+      STB_TRY(launch_pool_bwd(ctx->pooling, g[cur], at<bf16>(ctx, pl.act_off[i - 1]), g[cur ^ 1], pl.h[i - 1],
+                              pl.w[i - 1], kCout[i - 1], s));
+      ctx->prof.end(s);
+      cur ^= 1;
+      --np;
+    } else {
+      a.mode = 1;
+      a.mask_src = at<bf16>(ctx, pl.act_off[i - 1]);
+      for (int l = 0; l < 5; ++l)
+        if (kStyleConv[l] == i - 1) {
+          const W2Layer& L = ctx->w2.host_layers[l];
+          a.C2 = kStyleC[l]; a.A2 = at<bf16>(ctx, pl.act_off[i - 1]); a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
+        }
+      if (i - 1 == kContentConv) {
+        a.ctarget = at<bf16>(ctx, pl.ctarget_off);
+        a.cscale = 2.f * ctx->content_weight / (float)n22;
+      }
+      ctx->prof.begin(PC_CONV_BWD, s);
+      STB_TRY(launch_pixel_gemm(a, s));
+      ctx->prof.end(s);
+      cur ^= 1;
+    }
+  }
+  (void)np;
+  // ---- conv0 dgrad + TV gradient + Adam + clamp + EMA
+  AdamScalars as{};
+  if (apply_update) {
+    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    as.one_minus_b1 = 1.f - beta1; as.b2 = beta2; as.one_minus_b2 = 1.f - beta2;
+    as.step_size = (float)((double)lr / bc1);
+    as.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    as.eps = adam_eps; as.ema_decay = ema_decay; as.one_minus_decay = 1.f - ema_decay;
+  }
+  ctx->prof.begin(PC_CONV0_BWD_ADAM, s);
+  STB_TRY(launch_conv0_bwd_adam(g[cur], ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema, grad_out,
+                                H, W, as, apply_update, s));
+  ctx->prof.end(s);
+  ctx->prof.begin(PC_FINALIZE, s);
+  finalize_loss_kernel<<<1, 1024, 0, s>>>(at<float>(ctx, pl.ssep_off), n_sse, ctx->content_weight / (float)n22,
+                                          loss_dev + 16, at<float>(ctx, pl.tvp_off), pl.n_tv_partials,
+                                          ctx->tv_weight, loss_dev);
+  ctx->prof.end(s);
+  STB_CUDA_CHECK(cudaGetLastError());
+  if (loss_out_host8) STB_CUDA_CHECK(cudaMemcpyAsync(loss_out_host8, loss_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return STB_OK;
+}
+
+int stb_iterate(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
+                float beta1, float beta2, float adam_eps, float ema_decay, float* loss_out_host8, void* stream) {
+  return stb_iterate_ex(ctx, img, exp_avg, exp_avg_sq, ema, step, lr, beta1, beta2, adam_eps, ema_decay, 1, nullptr,
+                        loss_out_host8, stream);
+}
+
+// Per-kernel-class device timing (CUDA events on the launching stream).  enable: 1 starts recording spans for
+// subsequent calls; stb_profile_read synchronises the recorded events, returns accumulated milliseconds and span
+// counts per class (PC_* order: conv0_fwd_tv, conv_fwd, pool_fwd, gram, sse, w2, conv_bwd, pool_bwd,
+// conv0_bwd_adam, finalize) and clears the record.
+int stb_profile_enable(stb_ctx* ctx, int enable) {
+  STB_CHECK(ctx != nullptr, STB_ERR_INVALID, "null ctx");
+  ctx->prof.on = enable != 0;
+  ctx->prof.spans.clear();
+  ctx->prof.used = 0;
+  return STB_OK;
+}
+
+int stb_profile_read(stb_ctx* ctx, float* ms_out, int* count_out, int n_classes) {
+  STB_CHECK(ctx && ms_out && count_out && n_classes >= PC_COUNT, STB_ERR_INVALID, "bad argument");
+  for (int i = 0; i < n_classes; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (const auto& sp : ctx->prof.spans) {
+    if (sp.e1 < 0) continue;
+    STB_CUDA_CHECK(cudaEventSynchronize(ctx->prof.pool[sp.e1]));
+    float ms = 0.f;
+    STB_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->prof.pool[sp.e0], ctx->prof.pool[sp.e1]));
+    ms_out[sp.cls] += ms;
+    count_out[sp.cls] += 1;
+  }
+  ctx->prof.spans.clear();
+  ctx->prof.used = 0;
+  return STB_OK;
+}
+
+// test hook: copy an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward
+int stb_debug_activation(stb_ctx* ctx, int H, int W, int conv_index, void* out_bf16, size_t out_bytes, void* stream) {
+  STB_CHECK(ctx && out_bf16 && conv_index >= 0 && conv_index < NCONV, STB_ERR_INVALID, "bad argument");
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  const size_t bytes = (size_t)pl.h[conv_index] * pl.w[conv_index] * kCout[conv_index] * 2;
+  STB_CHECK(out_bytes >= bytes, STB_ERR_INVALID, "output buffer too small (%zu < %zu)", out_bytes, bytes);
+  STB_CUDA_CHECK(cudaMemcpyAsync(out_bf16, at<bf16>(ctx, pl.act_off[conv_index]), bytes, cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+  return STB_OK;
+}
+
+}  // extern "C"

@@ -36,3 +36,85 @@ int stb_test_pixel_gemm(int H, int W, int Cin, int Cout, int C2, int mode, const
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void* out_bf16, int H, int W,
+                       float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream) {
+  return launch_conv0_fwd(img, w0, b0, static_cast<bf16*>(out_bf16), H, W, tv_weight, gtv, tv_partials, n_partials,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
+                       void* stream) {
+  AdamScalars as{};
+  return launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), w0, gtv, nullptr, nullptr, nullptr, nullptr,
+                               grad_out, H, W, as, 0, static_cast<cudaStream_t>(stream));
+}
+
+int stb_test_pool(int pooling, int backward, const void* in_or_gout, const void* y, void* out, int H, int W, int C,
+                  void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!backward) return launch_pool_fwd(pooling, static_cast<const bf16*>(in_or_gout), static_cast<bf16*>(out), H, W, C, s);
+  return launch_pool_bwd(pooling, static_cast<const bf16*>(in_or_gout), static_cast<const bf16*>(y),
+                         static_cast<bf16*>(out), H, W, C, s);
+}
+
+size_t stb_test_gram_partials_floats(long P, int C) { return gram_partials_floats(P, C); }
+
+int stb_test_gram(const void* F_bf16, long P, int C, float* partials_ws, size_t partials_floats, float* S_raw,
+                  float* sums, void* stream) {
+  STB_CHECK(partials_floats >= gram_partials_floats(P, C), STB_ERR_WORKSPACE, "gram partials workspace too small");
+  return launch_gram(static_cast<const bf16*>(F_bf16), P, C, partials_ws, S_raw, sums,
+                     static_cast<cudaStream_t>(stream));
+}
+
+size_t stb_test_w2_workspace_bytes(void) { return W2Engine::workspace_bytes(); }
+
+// Runs the W2 engine with the given problem placed in the slot of matching size (other slots get a benign
+// identity problem).  Outputs: weighted loss, Gs = G + G^T (fp32, NOT divided by npix), gmu (not divided),
+// and the target's sqrtm(cov_t).
+int stb_test_w2(const float* mean_t, const float* srm_t, const float* S_raw, const float* sums, int C, float npix,
+                float weight, void* ws, size_t ws_bytes, float* loss_out, float* gs_out, float* gmu_out,
+                float* csqrt_out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static W2Engine eng;  // test-only
+  const int ns[5] = {64, 128, 256, 512, 512};
+  STB_TRY(eng.init(ws, ws_bytes, ns));
+  int slot = -1;
+  for (int l = 0; l < 5; ++l)
+    if (ns[l] == C) { slot = l; break; }
+  STB_CHECK(slot >= 0, STB_ERR_INVALID, "C must be one of 64,128,256,512");
+  // benign content for the other slots: srm = I, mean = 0, S_raw = I, sums = 0, npix = 1
+  for (int l = 0; l < 5; ++l) {
+    W2Layer& L = eng.host_layers[l];
+    const int n = L.n;
+    std::vector<float> eye((size_t)n * n, 0.f), zero(n, 0.f);
+    for (int i = 0; i < n; ++i) eye[(size_t)i * n + i] = 1.f;
+    L.weight = 1.f; L.npix = 1.f;
+    L.S_raw = L.X1;   // scratch matrices that the forward does not touch before reading S_raw
+    L.sums = L.gmu_bias;
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.srm_t, eye.data(), eye.size() * 4, cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.S_raw, eye.data(), eye.size() * 4, cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.mean_t, zero.data(), n * 4, cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaMemcpyAsync(L.sums, zero.data(), n * 4, cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  W2Layer& T = eng.host_layers[slot];
+  T.weight = weight; T.npix = npix;
+  STB_CUDA_CHECK(cudaMemcpyAsync(T.srm_t, srm_t, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(T.mean_t, mean_t, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(T.S_raw, S_raw, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(T.sums, sums, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_TRY(eng.upload_layers(s));
+  STB_TRY(eng.build_targets(s));
+  STB_TRY(eng.forward_backward(T.scal + 32, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(loss_out, T.scal + W2S_LOSS, 4, cudaMemcpyDeviceToDevice, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(gs_out, T.Gs, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_CUDA_CHECK(cudaMemcpyAsync(csqrt_out, T.P, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+  // gmu_bias holds gmu / npix
+  STB_CUDA_CHECK(cudaMemcpyAsync(gmu_out, T.gmu_bias, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  return STB_OK;
+}
+
+}  // extern "C"

@@ -237,6 +237,10 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               float b = __uint_as_float(v[2 * i + 1]) + s_bias[n0 + cb + 2 * i + 1];
               packed[i] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
             }
+          } else if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
           } else {
             uint4 yv[4], tv[4];
 #pragma unroll
@@ -337,6 +341,7 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   kp.a2_row0 = a.a2_row0;
   kp.bias = a.bias; kp.mask_src = a.mask_src; kp.ctarget = a.ctarget; kp.cscale = a.cscale;
   kp.row_lo = a.row_lo; kp.row_hi = a.row_hi;
+  STB_CHECK(a.mode >= 0 && a.mode <= 2, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
   if (a.mode == 1) STB_CHECK(a.mask_src != nullptr, STB_ERR_INVALID, "pixel_gemm: bwd needs mask_src");
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmOut;
@@ -357,10 +362,14 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
     if (BN == 256) return launch_cfg<256, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
     if (BN == 128) return launch_cfg<128, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
     return launch_cfg<64, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-  } else {
+  } else if (a.mode == 1) {
     if (BN == 256) return launch_cfg<256, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
     if (BN == 128) return launch_cfg<128, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
     return launch_cfg<64, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+  } else {
+    if (BN == 256) return launch_cfg<256, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+    if (BN == 128) return launch_cfg<128, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+    return launch_cfg<64, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
   }
 }
 

@@ -1,0 +1,225 @@
+// Second raw moment and channel sums of a pixel-major (NHWC bf16) activation on tcgen05:
+//     S_raw[i][j] = sum_p F[p][i] * F[p][j]        sums[i] = sum_p F[p][i]
+// i.e. the un-normalised `einsum('...chw,...dhw->...cd')` and `mean([-2,-1])` of StyleLossW2.get_target
+// (/root/reference/style_transfer/style_transfer.py:163-168).  K is the pixel axis (up to 4.2 M), so the GEMM is
+// split-K: CTA (tile, split) accumulates a 128 x BN fp32 tile in TMEM over its pixel range and writes a partial;
+// gram_reduce sums the partials in a fixed order (deterministic).
+//
+// Both operands are the SAME pixel-major smem tiles read "MN-major" (channel contiguous, SW128): no transpose is
+// ever materialised.  Channel sums ride along as one extra N=16 MMA per k-step against a constant tile of ones.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace stb {
+
+namespace {
+
+constexpr int PK = 64;                 // pixels per pipeline stage
+constexpr int ATOM_BYTES = PK * 128;   // 64 channels x PK pixels, bf16
+constexpr int G_STAGES = 4;
+constexpr int G_THREADS = 64 + 128;
+
+template <int BN>
+struct GCfg {
+  static constexpr int B_ATOMS = BN / 64;
+  static constexpr int STAGE_BYTES = (B_ATOMS + 2) * ATOM_BYTES;
+  static constexpr int OFF_ONES = G_STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_ONES + 2048;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + (2 * G_STAGES + 1) * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;
+  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
+};
+
+struct GParams {
+  long P;              // number of pixels
+  int C;
+  int n_tj;            // column tiles
+  long chunk_per_split;  // pixels per split (multiple of PK)
+  float* partials;     // [n_splits][C][C]
+  float* sum_partials; // [n_splits][C]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
+  using C = GCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* empty = full + G_STAGES;
+  uint64_t* t_full = empty + G_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ti = blockIdx.x / p.n_tj, tj = blockIdx.x % p.n_tj;
+  const int split = blockIdx.y;
+  const int i0 = ti * 128, j0 = tj * BN;
+  const int m_valid = min(128, p.C - i0);
+  const bool contained = (i0 >= j0) && (i0 + m_valid <= j0 + BN);
+  const long p_begin = (long)split * p.chunk_per_split;
+  const long p_end = min(p.P, p_begin + p.chunk_per_split);
+  const int n_k = (int)((p_end - p_begin + PK - 1) / PK);
+
+  // constant ones tile (bf16 1.0 = 0x3F80)
+  for (int i = threadIdx.x; i < 2048 / 4; i += G_THREADS)
+    reinterpret_cast<uint32_t*>(smem + C::OFF_ONES)[i] = 0x3F803F80u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmF);
+    for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  fence_proxy_async_smem();  // ones tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (C::B_ATOMS + (contained ? 0 : 2)) * ATOM_BYTES;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < n_k; ++k) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], tx_bytes);
+        uint8_t* st = smem + s * C::STAGE_BYTES;
+        const int pix = (int)(p_begin + (long)k * PK);
+        for (int b = 0; b < C::B_ATOMS; ++b) tma_load_3d(st + b * ATOM_BYTES, &tmF, &full[s], j0 + b * 64, pix, 0);
+        if (!contained)
+          for (int a = 0; a < 2; ++a)
+            tma_load_3d(st + (C::B_ATOMS + a) * ATOM_BYTES, &tmF, &full[s], i0 + a * 64, pix, 0);
+        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = umma_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t idesc_sum = umma_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones_addr = smem_u32(smem + C::OFF_ONES);
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int k = 0; k < n_k; ++k) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t a_addr = contained ? b_addr + ((i0 - j0) >> 6) * ATOM_BYTES : b_addr + C::B_ATOMS * ATOM_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < PK / 16; ++ks) {
+          // MN-major SW128: LBO = stride between 64-channel atoms, SBO = stride between 8-pixel groups
+          const uint64_t da = umma_desc_sw128(a_addr + ks * 2048, ATOM_BYTES, 1024);
+          const uint64_t db = umma_desc_sw128(b_addr + ks * 2048, ATOM_BYTES, 1024);
+          umma_bf16(tmem_base, da, db, idesc_main, accum);
+          if (tj == 0) umma_bf16(tmem_base + BN, da, umma_desc_sw128(ones_addr, 1024, 1024), idesc_sum, accum);
+          accum = 1;
+        }
+        umma_commit(&empty[s]);
+        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(t_full);
+    }
+    __syncwarp();
+  } else {
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const bool valid = r < m_valid;
+    float* dst = p.partials + ((size_t)split * p.C + (i0 + r)) * p.C + j0;
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + cb, v);
+      tmem_ld_wait();
+      if (valid && n_k > 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(dst + cb + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                          __uint_as_float(v[4 * q + 3]));
+      }
+    }
+    if (tj == 0) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + BN, v);
+      tmem_ld_wait();
+      if (valid && n_k > 0) p.sum_partials[(size_t)split * p.C + i0 + r] = __uint_as_float(v[0]);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// sum partials in split order: out[i] = sum_s part[s][i]
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int n_splits) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < n_splits; ++k) s += part[(size_t)k * n + i];
+    out[i] = s;
+  }
+}
+
+template <int BN>
+int launch_gram_cfg(const CUtensorMap& tm, const GParams& gp, int n_tiles, int n_splits, cudaStream_t stream) {
+  using C = GCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gram_kernel<BN>;
+  if (!attr_set) {
+    STB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<dim3(n_tiles, n_splits), G_THREADS, C::SMEM_BYTES, stream>>>(tm, gp);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+}  // namespace
+
+int gram_num_splits(long P, int C) {
+  const int BN = C >= 256 ? 256 : C;
+  const int n_tiles = ((C + 127) / 128) * (C / BN);
+  long chunks = (P + PK - 1) / PK;
+  long want = (2L * num_sms() + n_tiles - 1) / n_tiles;  // ~2 CTAs' worth of splits per SM-slot
+  if (want > chunks) want = chunks;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  // make every split non-empty
+  long per = (chunks + want - 1) / want;
+  long n = (chunks + per - 1) / per;
+  return (int)n;
+}
+
+size_t gram_partials_floats(long P, int C) { return (size_t)gram_num_splits(P, C) * ((size_t)C * C + C); }
+
+int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream) {
+  STB_CHECK(C % 64 == 0 && C <= 512 && P > 0, STB_ERR_INVALID, "gram: C=%d P=%ld", C, P);
+  const int BN = C >= 256 ? 256 : C;
+  const int n_tj = C / BN;
+  const int n_ti = (C + 127) / 128;
+  const int n_splits = gram_num_splits(P, C);
+  const long chunks = (P + PK - 1) / PK;
+  const long per = (chunks + n_splits - 1) / n_splits;
+  GParams gp;
+  gp.P = P; gp.C = C; gp.n_tj = n_tj; gp.chunk_per_split = per * PK;
+  gp.partials = partials_ws;
+  gp.sum_partials = partials_ws + (size_t)n_splits * C * C;
+  CUtensorMap tm;
+  STB_TRY(make_tmap_bf16_3d(&tm, F, C, (uint64_t)P, 1, C * 2ull, (uint64_t)P * C * 2ull, 64, PK, 1));
+  if (BN == 256) STB_TRY(launch_gram_cfg<256>(tm, gp, n_ti * n_tj, n_splits, stream));
+  else if (BN == 128) STB_TRY(launch_gram_cfg<128>(tm, gp, n_ti * n_tj, n_splits, stream));
+  else STB_TRY(launch_gram_cfg<64>(tm, gp, n_ti * n_tj, n_splits, stream));
+  const long nn = (long)C * C;
+  int g = (int)((nn + 255) / 256);
+  gram_reduce_kernel<<<g, 256, 0, stream>>>(gp.partials, S_raw, nn, n_splits);
+  gram_reduce_kernel<<<(C + 255) / 256, 256, 0, stream>>>(gp.sum_partials, sums, C, n_splits);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+}  // namespace stb

@@ -1,0 +1,452 @@
+// HBM-bound kernels on either side of the tensor-core trunk:
+//   conv0_fwd_tv   : Normalize (ST:30-31,85) + replicate-pad conv 3->64 + bias + ReLU (ST:39,52-59) -> bf16 NHWC,
+//                    fused with the nine-point TV loss and its gradient on the raw image (ST:184-195)
+//   conv0_bwd_adam : conv0 dgrad (adjoint of replicate pad) + Normalize backward + TV gradient -> Adam step
+//                    (torch/optim/adam.py:413-546 single-tensor math) -> clamp_(0,1) (ST:483-485) -> EMA (ST:250-253)
+//   pool2x2 fwd/bwd: MaxPool2d(2) / Scale(AvgPool2d(2),2.0) / Scale(LPPool2d(2,2),0.78)  (ST:21-22,41-46)
+//   content_sse    : sum((F22 - T)^2)  (ST:119-126)
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace stb {
+
+namespace {
+
+__constant__ float c_mean[3] = {0.485f, 0.456f, 0.406f};
+__constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------------------------------------ conv0 fwd + TV
+// grid: (ceil(W/64), H); block 256 = 64 pixels x 4 channel groups of 16.
+struct TvConst {
+  float k1, k3;        // gradient factors 4/(3 n1), 4/(12 n3) times tv_weight
+  float l1, l3;        // loss factors 2/(3 n1), 2/(12 n3)
+};
+
+// gradient of the (unweighted) TV sum w.r.t. the replicate-padded grid position (a,b) of channel plane `x`
+// (padded coordinates: pixel (y,x) sits at (y+1,x+1)); general (slow) path used for border folds only.
+__device__ float tv_gpad_slow(const float* __restrict__ x, int H, int W, int a, int b, float k1, float k3) {
+  auto P = [&](int i, int j) { return __ldg(x + (size_t)clampi(i - 1, 0, H - 1) * W + clampi(j - 1, 0, W - 1)); };
+  float g = 0.f;
+  const float c = P(a, b);
+  // e3[i][j] = P[i+1][j+1]-P[i][j], i in [0,H], j in [0,W]
+  if (a >= 1 && b >= 1) g += k3 * (c - P(a - 1, b - 1));
+  if (a <= H && b <= W) g -= k3 * (P(a + 1, b + 1) - c);
+  // e4[i][j] = P[i+1][j]-P[i][j+1]
+  if (a >= 1 && b <= W) g += k3 * (c - P(a - 1, b + 1));
+  if (a <= H && b >= 1) g -= k3 * (P(a + 1, b - 1) - c);
+  // e1[y][x] = P[y+1][x+2]-P[y+1][x+1], rows a in [1,H]
+  if (a >= 1 && a <= H) {
+    if (b >= 2) g += k1 * (c - P(a, b - 1));
+    if (b >= 1 && b <= W) g -= k1 * (P(a, b + 1) - c);
+  }
+  // e2[y][x] = P[y+2][x+1]-P[y+1][x+1], cols b in [1,W]
+  if (b >= 1 && b <= W) {
+    if (a >= 2) g += k1 * (c - P(a - 1, b));
+    if (a >= 1 && a <= H) g -= k1 * (P(a + 1, b) - c);
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(256)
+conv0_fwd_tv_kernel(const float* __restrict__ img, const float* __restrict__ w0, const float* __restrict__ b0,
+                    bf16* __restrict__ out, int H, int W, int do_tv, TvConst tc, float* __restrict__ gtv,
+                    float* __restrict__ tv_partials) {
+  __shared__ __align__(16) float s_w[27 * 64];  // [k = (c*3+ky)*3+kx][co]
+  __shared__ float s_b[64];
+  __shared__ float s_red[8];
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) {
+    const int co = i & 63, k = i >> 6;
+    s_w[i] = w0[co * 27 + k];
+  }
+  if (threadIdx.x < 64) s_b[threadIdx.x] = b0[threadIdx.x];
+  __syncthreads();
+
+  const int y = blockIdx.y;
+  const int x = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = threadIdx.x & 3;
+  float tv_local = 0.f;
+  if (x < W) {
+    float raw[3][3][3];
+    const int ys[3] = {clampi(y - 1, 0, H - 1), y, clampi(y + 1, 0, H - 1)};
+    const int xs[3] = {clampi(x - 1, 0, W - 1), x, clampi(x + 1, 0, W - 1)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) raw[c][i][j] = __ldg(img + ((size_t)c * H + ys[i]) * W + xs[j]);
+
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = s_b[cg * 16 + i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float v = (raw[c][i][j] - c_mean[c]) / c_std[c];
+          const float4* wp = reinterpret_cast<const float4*>(&s_w[((c * 3 + i) * 3 + j) * 64 + cg * 16]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wp[q];
+            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+          }
+        }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * W + x) * 64 + cg * 16);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+
+    if (do_tv && cg < 3) {
+      // channel cg of this pixel: TV loss share + gradient (fast path from the 3x3 raw neighbourhood)
+      const int c = cg;
+      const float(*n)[3] = raw[c];
+      const float ctr = n[1][1];
+      const bool hasL = x > 0, hasR = x < W - 1, hasU = y > 0, hasD = y < H - 1;
+      // owned loss entries: e1[y][x], e2[y][x], e3[y][x], e4[y][x] (+ the extra row i=H / col j=W at the far borders)
+      const float e1 = n[1][2] - ctr, e2 = n[2][1] - ctr;
+      // e3[i][j] = X[c(i)][c(j)] - X[c(i-1)][c(j-1)] at (i,j)=(y,x):  ctr - n[0][0]
+      const float e3 = ctr - n[0][0];
+      // e4[i][j] = X[c(i)][c(j-1)] - X[c(i-1)][c(j)] at (y,x): n[1][0] - n[0][1]
+      const float e4 = n[1][0] - n[0][1];
+      float l = tc.l1 * (e1 * e1 + e2 * e2) + tc.l3 * (e3 * e3 + e4 * e4);
+      if (!hasD) {  // row i = H: X[H-1][c(j)] - X[H-1][c(j-1)]  and  X[H-1][c(j-1)] - X[H-1][c(j)]
+        const float d = ctr - n[1][0];
+        l += tc.l3 * (d * d + d * d);
+      }
+      if (!hasR) {  // col j = W: X[c(i)][W-1] - X[c(i-1)][W-1]  and  X[c(i)][W-1] - X[c(i-1)][W-1] (e4 sign flipped)
+        const float d = ctr - n[0][1];
+        l += tc.l3 * (d * d + d * d);
+      }
+      // corner entry (i=H, j=W) is identically zero
+      tv_local = l;
+      float g;
+      if (hasL && hasR && hasU && hasD) {
+        g = tc.k1 * (4.f * ctr - n[1][0] - n[1][2] - n[0][1] - n[2][1]) +
+            tc.k3 * (4.f * ctr - n[0][0] - n[2][2] - n[0][2] - n[2][0]);
+      } else {
+        const float* plane = img + (size_t)c * H * W;
+        g = 0.f;
+        for (int a = (hasU ? y + 1 : 0); a <= (hasD ? y + 1 : H + 1); ++a)
+          for (int b = (hasL ? x + 1 : 0); b <= (hasR ? x + 1 : W + 1); ++b)
+            g += tv_gpad_slow(plane, H, W, a, b, tc.k1, tc.k3);
+      }
+      gtv[((size_t)c * H + y) * W + x] = g;
+    }
+  }
+  if (do_tv) {
+    float s = warp_sum(tv_local);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += s_red[i];
+      tv_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv0 bwd + Adam
+// 8 lanes per pixel (8 channels of g0 each); a warp covers 4 consecutive pixels of a row.
+__device__ __forceinline__ void conv0_gpad(const bf16* __restrict__ g0, const float* __restrict__ s_w, int H, int W,
+                                           int a, int b, int sub, float (&acc)[3]) {
+  // gradient on the replicate-padded grid position (a,b): sum over taps of g0[a-ky][b-kx][:] . W[:, c, ky, kx]
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yo = a - ky;
+    if (yo < 0 || yo >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xo = b - kx;
+      if (xo < 0 || xo >= W) continue;
+      const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g0 + ((size_t)yo * W + xo) * 64 + sub * 8));
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      float gf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { gf[2 * i] = bf16lo(gw[i]); gf[2 * i + 1] = bf16hi(gw[i]); }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[((ky * 3 + kx) * 3 + c) * 64 + sub * 8]);
+        const float4 w0 = wp[0], w1 = wp[1];
+        acc[c] = fmaf(gf[0], w0.x, acc[c]); acc[c] = fmaf(gf[1], w0.y, acc[c]);
+        acc[c] = fmaf(gf[2], w0.z, acc[c]); acc[c] = fmaf(gf[3], w0.w, acc[c]);
+        acc[c] = fmaf(gf[4], w1.x, acc[c]); acc[c] = fmaf(gf[5], w1.y, acc[c]);
+        acc[c] = fmaf(gf[6], w1.z, acc[c]); acc[c] = fmaf(gf[7], w1.w, acc[c]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const float* __restrict__ w0, const float* __restrict__ gtv,
+                      float* __restrict__ img, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                      float* __restrict__ ema, float* __restrict__ grad_out, int H, int W, AdamScalars ac,
+                      int apply_update) {
+  __shared__ __align__(16) float s_w[27 * 64];  // [(ky*3+kx)*3 + c][co]
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) {
+    const int co = i & 63, k = i >> 6;
+    const int c = k % 3, tap = k / 3;
+    s_w[i] = w0[(co * 3 + c) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const long gp = ((long)blockIdx.x * 256 + threadIdx.x) >> 3;  // global pixel id
+  const long total = (long)H * W;
+  const bool valid = gp < total;
+  const int y = valid ? (int)(gp / W) : 0, x = valid ? (int)(gp % W) : 0;
+  float acc[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+    const int a0 = (y == 0) ? 0 : y + 1, a1 = (y == H - 1) ? H + 1 : y + 1;
+    const int b0 = (x == 0) ? 0 : x + 1, b1 = (x == W - 1) ? W + 1 : x + 1;
+    for (int a = a0; a <= a1; ++a)
+      for (int b = b0; b <= b1; ++b) conv0_gpad(g0, s_w, H, W, a, b, sub, acc);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+  }
+  if (valid && sub < 3) {
+    const int c = sub;
+    const size_t idx = ((size_t)c * H + y) * W + x;
+    const float gsel = (c == 0) ? acc[0] : ((c == 1) ? acc[1] : acc[2]);
+    const float g = gsel / c_std[c] + (gtv ? gtv[idx] : 0.f);
+    if (grad_out) grad_out[idx] = g;
+    if (apply_update) {
+      float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
+      m = m + (g - m) * ac.one_minus_b1;
+      v = v * ac.b2 + ac.one_minus_b2 * g * g;
+      const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
+      p = p - ac.step_size * (m / denom);
+      p = fminf(fmaxf(p, 0.f), 1.f);
+      e = e * ac.ema_decay + ac.one_minus_decay * p;
+      exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+// one thread = one output pixel x 8 channels (16 B); NHWC bf16.
+template <int POOL>
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long total = (long)Ho * Wo * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = i % C8;
+    const long p = i / C8;
+    const int xo = p % Wo, yo = p / Wo;
+    const bf16* base = in + ((size_t)(2 * yo) * W + 2 * xo) * C + c8 * 8;
+    uint4 v[4];
+    v[0] = __ldg(reinterpret_cast<const uint4*>(base));
+    v[1] = __ldg(reinterpret_cast<const uint4*>(base + C));
+    v[2] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C));
+    v[3] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C + C));
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo[4], hi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u = reinterpret_cast<const uint32_t*>(&v[q])[k];
+        lo[q] = bf16lo(u);
+        hi[q] = bf16hi(u);
+      }
+      float a, b;
+      if (POOL == STB_POOL_MAX) {
+        a = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
+        b = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+      } else if (POOL == STB_POOL_AVERAGE) {
+        a = (lo[0] + lo[1] + lo[2] + lo[3]) * 0.25f * 2.0f;
+        b = (hi[0] + hi[1] + hi[2] + hi[3]) * 0.25f * 2.0f;
+      } else {
+        a = sqrtf(lo[0] * lo[0] + lo[1] * lo[1] + lo[2] * lo[2] + lo[3] * lo[3]) * 0.78f;
+        b = sqrtf(hi[0] * hi[0] + hi[1] * hi[1] + hi[2] * hi[2] + hi[3] * hi[3]) * 0.78f;
+      }
+      r[k] = pack_bf16x2(a, b);
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)yo * Wo + xo) * C + c8 * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// backward through pool + the ReLU that produced the pool input y:  gin = pool_bwd(gout; y) * (y > 0).
+// One thread = one 2x2 input window x 8 channels; windows beyond the floor-mode extent write zeros.
+template <int POOL>
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const bf16* __restrict__ gout, const bf16* __restrict__ y, bf16* __restrict__ gin, int H, int W,
+                int C) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;  // windows incl. the ragged last row / column
+  const long total = (long)Hc * Wc * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = i % C8;
+    const long p = i / C8;
+    const int xo = p % Wc, yo = p / Wc;
+    const bool full = (yo < Ho) && (xo < Wo);
+    if (!full) {
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const int yy = 2 * yo + dy, xx = 2 * xo + dx;
+          if (yy < H && xx < W && !(yy < 2 * Ho && xx < 2 * Wo))
+            *reinterpret_cast<uint4*>(gin + ((size_t)yy * W + xx) * C + c8 * 8) = make_uint4(0, 0, 0, 0);
+        }
+      // (positions of a ragged window that still belong to a full window do not exist: windows are disjoint)
+      continue;
+    }
+    const size_t ibase = ((size_t)(2 * yo) * W + 2 * xo) * C + c8 * 8;
+    const size_t offs[4] = {0, (size_t)C, (size_t)W * C, (size_t)W * C + C};
+    uint4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const uint4*>(y + ibase + offs[q]));
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gout + ((size_t)yo * Wo + xo) * C + c8 * 8));
+    uint32_t r[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t gu = reinterpret_cast<const uint32_t*>(&gv)[k];
+      float gq[2] = {bf16lo(gu), bf16hi(gu)};
+      float xin[2][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u = reinterpret_cast<const uint32_t*>(&v[q])[k];
+        xin[0][q] = bf16lo(u);
+        xin[1][q] = bf16hi(u);
+      }
+      float o[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (POOL == STB_POOL_MAX) {
+          const float m = fmaxf(fmaxf(xin[h][0], xin[h][1]), fmaxf(xin[h][2], xin[h][3]));
+          bool taken = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool sel = (xin[h][q] == m) && !taken;  // first maximum in scan order wins (ATen)
+            taken = taken || sel;
+            o[h][q] = (sel && xin[h][q] > 0.f) ? gq[h] : 0.f;
+          }
+        } else if (POOL == STB_POOL_AVERAGE) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[h][q] = xin[h][q] > 0.f ? gq[h] * 0.5f : 0.f;
+        } else {
+          const float s = sqrtf(xin[h][0] * xin[h][0] + xin[h][1] * xin[h][1] + xin[h][2] * xin[h][2] +
+                                xin[h][3] * xin[h][3]);
+          const float inv = s > 0.f ? 0.78f / s : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[h][q] = xin[h][q] > 0.f ? gq[h] * xin[h][q] * inv : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q][k] = pack_bf16x2(o[0][q], o[1][q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(gin + ibase + offs[q]) = make_uint4(r[q][0], r[q][1], r[q][2], r[q][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ content SSE
+__global__ void __launch_bounds__(256)
+sse_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long n8, float* __restrict__ partials) {
+  __shared__ float s_red[8];
+  float s = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const uint4 av = __ldg(reinterpret_cast<const uint4*>(a) + i);
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(b) + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t au = reinterpret_cast<const uint32_t*>(&av)[k], bu = reinterpret_cast<const uint32_t*>(&bv)[k];
+      const float d0 = bf16lo(au) - bf16lo(bu), d1 = bf16hi(au) - bf16hi(bu);
+      s = fmaf(d0, d0, s);
+      s = fmaf(d1, d1, s);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    partials[blockIdx.x] = t;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ launchers
+int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* out, int H, int W, float tv_weight,
+                     float* gtv, float* tv_partials, int* n_partials, cudaStream_t s) {
+  dim3 grid((W + 63) / 64, H);
+  TvConst tc{};
+  const int do_tv = gtv != nullptr;
+  if (do_tv) {
+    const double n1 = 3.0 * H * W, n3 = 3.0 * (H + 1.0) * (W + 1.0);
+    tc.k1 = (float)(tv_weight * 4.0 / (3.0 * n1));
+    tc.k3 = (float)(tv_weight * 4.0 / (12.0 * n3));
+    tc.l1 = (float)(2.0 / (3.0 * n1));
+    tc.l3 = (float)(2.0 / (12.0 * n3));
+  }
+  if (n_partials) *n_partials = grid.x * grid.y;
+  conv0_fwd_tv_kernel<<<grid, 256, 0, s>>>(img, w0, b0, out, H, W, do_tv, tc, gtv, tv_partials);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int launch_conv0_bwd_adam(const bf16* g0, const float* w0, const float* gtv, float* img, float* exp_avg,
+                          float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars& a,
+                          int apply_update, cudaStream_t s) {
+  const long threads = (long)H * W * 8;
+  const int blocks = (int)((threads + 255) / 256);
+  conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a,
+                                               apply_update);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+static int grid_for(long work_items, int block) {
+  long b = (work_items + block - 1) / block;
+  const long cap = (long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s) {
+  const long total = (long)(H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return STB_OK;
+  const int g = grid_for(total, 256);
+  if (pooling == STB_POOL_MAX) pool_fwd_kernel<STB_POOL_MAX><<<g, 256, 0, s>>>(in, out, H, W, C);
+  else if (pooling == STB_POOL_AVERAGE) pool_fwd_kernel<STB_POOL_AVERAGE><<<g, 256, 0, s>>>(in, out, H, W, C);
+  else pool_fwd_kernel<STB_POOL_L2><<<g, 256, 0, s>>>(in, out, H, W, C);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s) {
+  const long total = (long)((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  const int g = grid_for(total, 256);
+  if (pooling == STB_POOL_MAX) pool_bwd_kernel<STB_POOL_MAX><<<g, 256, 0, s>>>(gout, y, gin, H, W, C);
+  else if (pooling == STB_POOL_AVERAGE) pool_bwd_kernel<STB_POOL_AVERAGE><<<g, 256, 0, s>>>(gout, y, gin, H, W, C);
+  else pool_bwd_kernel<STB_POOL_L2><<<g, 256, 0, s>>>(gout, y, gin, H, W, C);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s) {
+  const long n8 = n / 8;
+  int g = grid_for(n8, 256);
+  if (g > 1024) g = 1024;
+  if (n_partials) *n_partials = g;
+  sse_kernel<<<g, 256, 0, s>>>(a, b, n8, partials);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+}  // namespace stb

@@ -3,6 +3,8 @@
 //   image, Adam moments, EMA        : the reference's own NCHW fp32 [1,3,H,W] torch tensors
 //   conv weights                    : packed bf16 [tap][N][K] (K contiguous), see pack_weights_*
 #pragma once
+#include <vector>
+
 #include "host_util.h"
 
 namespace stb {
@@ -14,6 +16,7 @@ typedef __nv_bfloat16 bf16;
 //   fwd  (mode 0): + bias[n], ReLU                       (VGG conv 3x3 + bias + ReLU; ST:86-89 -> torchvision vgg.py)
 //   bwd  (mode 1): + bias[n] (rows in [row_lo,row_hi)), + cscale*(y - ctarget), * (y > 0)
 //                                                         (conv dgrad + tap-gradient GEMM + ReLU mask; autograd of ST:475)
+//   lin  (mode 2): none (dgrad whose consumer is the pool backward)
 struct PixelGemmArgs {
   int H = 0, W = 0;
   int Cin = 0;    // main 3x3 source channels (multiple of 64) or 0
@@ -37,5 +40,67 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream);
 // fp32 OIHW [Cout][Cin][3][3] -> bf16 [9][Cout][Cin] (fwd) / [9][Cin][Cout] with 180-degree rotated taps (dgrad)
 int pack_weights_fwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
 int pack_weights_bwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s);
+
+// ---------------------------------------------------------------- image-space / pooling kernels (image_ops.cu)
+struct AdamScalars {  // torch/optim/adam.py:413-546 scalars, evaluated on the host in double like torch does
+  float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps, ema_decay, one_minus_decay;
+};
+// gtv == nullptr: features-only forward (no TV).  tv_partials gets one float per CTA (n_partials of them).
+int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* out, int H, int W, float tv_weight,
+                     float* gtv, float* tv_partials, int* n_partials, cudaStream_t s);
+// g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  grad_out (optional) receives d loss/d image.
+int launch_conv0_bwd_adam(const bf16* g0, const float* w0, const float* gtv, float* img, float* exp_avg,
+                          float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars& a,
+                          int apply_update, cudaStream_t s);
+int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s);
+int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s);
+int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s);
+
+// ---------------------------------------------------------------- Gram / channel sums on tcgen05 (gram_tc.cu)
+int gram_num_splits(long P, int C);
+size_t gram_partials_floats(long P, int C);
+// F: [P][C] bf16 pixel-major.  S_raw [C][C] and sums [C] receive the un-normalised sums over the P pixels.
+int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
+
+// ---------------------------------------------------------------- W2 style loss engine, fp32 (w2.cu)
+struct GemmProb {  // D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I, all n x n row-major fp32
+  const float *A, *B, *A2, *B2, *Cadd;
+  float* D;
+  int n, transA, transB, transA2, transB2;
+  float alpha, alpha2, beta, gamma;
+};
+enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };
+struct W2Layer {
+  int n;            // channels
+  float eps;        // 1e-4 (ST:152)
+  float weight;     // style layer weight (ST:320-322)
+  float npix;       // number of pixels the raw sums were taken over (global count under multi-GPU)
+  float *S_raw, *sums;                 // inputs: reduced raw second moment [n][n] and channel sums [n]
+  float *mu, *cov;                     // current mean / covariance
+  float *mean_t, *srm_t, *cov_t, *P;   // target: mean, second raw moment, covariance, sqrtm(cov_t)
+  float *M, *X, *Y[2], *Z[2], *T;      // forward chain
+  float *A[2], *Q[2], *E, *X1, *X23, *U, *Gc, *Gs;  // backward chain
+  float* gmu_bias;  // out: (d loss / d mean) / npix              -> per-channel bias of the tap-gradient GEMM
+  bf16* gs_bf16;    // out: (G + G^T) / npix as bf16 [n][n]       -> B operand of the tap-gradient GEMM
+  float* scal;      // W2S_* scalars
+};
+struct W2Round { int first_tile, n_tiles; };
+struct W2Engine {
+  W2Layer host_layers[5];
+  W2Layer* d_layers = nullptr;
+  GemmProb* d_probs = nullptr;
+  uint32_t* d_tiles = nullptr;
+  std::vector<GemmProb> host_probs;
+  std::vector<W2Round> rounds;
+  int r_target_begin = 0, r_target_end = 0, r_fwd_begin = 0, r_fwd_ns_begin = 0, r_fwd_end = 0, r_bwd_begin = 0,
+      r_bwd_end = 0, gc_prob_first = 0;
+  static size_t layer_floats(int n);
+  static size_t workspace_bytes();
+  int init(void* ws, size_t bytes, const int n_per_layer[5]);
+  int upload_layers(cudaStream_t s);           // after editing host_layers (weights, npix, S_raw/sums pointers)
+  int run_rounds(int r0, int r1, cudaStream_t s);
+  int build_targets(cudaStream_t s);            // mean_t/srm_t -> cov_t, P = sqrtm_ns(cov_t)   (ST:152-160)
+  int forward_backward(float* loss_terms, cudaStream_t s);  // S_raw/sums -> loss_terms[5], gs_bf16, gmu_bias
+};
 
 }  // namespace stb

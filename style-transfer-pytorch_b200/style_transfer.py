@@ -1,0 +1,393 @@
+"""Drop-in `StyleTransfer` whose per-iteration body is one call into libstb200 (hand-written sm_100a CUDA).
+
+Public surface mirrors /root/reference/style_transfer/style_transfer.py ("ST"): `StyleTransfer(devices, pooling)`
+(ST:310), attributes (ST:311-324), `get_image_tensor` / `get_image` (ST:335-347), `stylize(...)` with the same
+keyword-only signature, defaults and annotations (ST:349-363; the CLI scrapes them, cli.py:150-153), `STIterate`
+(ST:298-306) and the synchronous per-iteration callback (ST:487-493).  Host-side work that is per *scale*, not per
+iteration (PIL resizes, init modes, bicubic warm start of the Adam moments) stays in PyTorch; everything inside
+the iteration loop (ST:472-486) runs in the native library.  There is no CPU or autograd fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+from PIL import Image
+from torch.nn import functional as F
+
+from . import _lib
+
+CONV_CHANNELS = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 256), (256, 256),
+                 (256, 512), (512, 512), (512, 512), (512, 512), (512, 512)]
+VGG19_CONV_INDICES = [0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28]
+STYLE_CHANNELS = [64, 128, 256, 512, 512]
+
+
+@dataclass
+class STIterate:
+    w: int
+    h: int
+    i: int
+    i_max: int
+    loss: float
+    time: float
+    gpu_ram: int
+
+
+def size_to_fit(size, max_dim, scale_up=False):
+    """Aspect-preserving (w, h) whose longer side is max_dim (ST:256-265)."""
+    w, h = size
+    if max(w, h) <= max_dim and not scale_up:
+        return w, h
+    if h > w:
+        return round(max_dim * w / h), max_dim
+    return max_dim, round(max_dim * h / w)
+
+
+def gen_scales(start, end):
+    """Pyramid of scales end / 2^(i/2) down to start, ascending (ST:268-276)."""
+    out = set()
+    i, scale = 0, end
+    while scale >= start:
+        out.add(scale)
+        i += 1
+        scale = round(end / pow(2, i / 2))
+    return sorted(out)
+
+
+def _resize(x, hw, mode):
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', UserWarning)
+        return F.interpolate(x, hw, mode=mode)
+
+
+def _pil_to_tensor(img):
+    arr = np.asarray(img.convert('RGB'), dtype=np.uint8)
+    return torch.from_numpy(arr.copy()).permute(2, 0, 1).to(torch.float32).div_(255).unsqueeze(0).contiguous()
+
+
+def load_vgg19_conv_weights():
+    """The thirteen conv (weight, bias) pairs of torchvision vgg19 IMAGENET1K_V1 features[:30] (as ST:35)."""
+    from torchvision import models
+    feats = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1).features
+    return [(feats[i].weight.detach().clone(), feats[i].bias.detach().clone()) for i in VGG19_CONV_INDICES]
+
+
+class EMA:
+    """Bias-corrected exponential moving average of the iterate (ST:237-253); `value` is updated in place by the
+    native iteration, only the scalar `accum` lives on the host."""
+
+    def __init__(self, input, decay):
+        self.decay = float(decay)
+        self.accum = self.decay
+        self.value = input.detach() * (1 - self.decay)
+
+    def get(self):
+        return self.value / (1 - self.accum)
+
+    def note_update(self):
+        self.accum *= self.decay
+
+
+class NativeVGG:
+    """Holder of the frozen VGG-19 conv stack and the native context built from it (replaces VGGFeatures, ST:20-90)."""
+
+    def __init__(self, conv_weights, pooling, device):
+        if pooling not in _lib.POOLING:
+            raise KeyError(pooling)
+        if len(conv_weights) != 13:
+            raise ValueError('expected 13 (weight, bias) pairs for vgg19.features[:30]')
+        self.pooling = pooling
+        self.device = device
+        self.weights = []
+        for (w, b), (cin, cout) in zip(conv_weights, CONV_CHANNELS):
+            if tuple(w.shape) != (cout, cin, 3, 3) or tuple(b.shape) != (cout,):
+                raise ValueError(f'bad conv parameter shape {tuple(w.shape)} / {tuple(b.shape)}')
+            self.weights.append((w.detach().to(device, torch.float32).contiguous(),
+                                 b.detach().to(device, torch.float32).contiguous()))
+        self.lib = _lib.load()
+        self.ctx = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            wp, _k1 = _lib.ptr_array([w for w, _ in self.weights])
+            bp, _k2 = _lib.ptr_array([b for _, b in self.weights])
+            _lib.check(self.lib.stb_ctx_create(device.index or 0, _lib.POOLING[pooling], wp, bp, _lib.cur_stream(),
+                                               ctypes.byref(self.ctx)))
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ctx', None) and self.ctx.value:
+                self.lib.stb_ctx_destroy(self.ctx)
+                self.ctx = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ workspace
+    def workspace_bytes(self, h, w):
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.stb_workspace_bytes(self.ctx, h, w, ctypes.byref(n)))
+        return n.value
+
+    def ensure_workspace(self, sizes):
+        """Bind a torch-owned workspace large enough for every (h, w) in sizes.  Returns True if (re)bound."""
+        need = max(self.workspace_bytes(h, w) for h, w in sizes)
+        if self._ws is not None and self._ws.numel() >= need + 1024:
+            return False
+        self._ws = None
+        self._ws = torch.empty(need + 2048, dtype=torch.uint8, device=self.device)
+        base = self._ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        _lib.check(self.lib.stb_bind_workspace(self.ctx, ctypes.c_void_p(aligned), need, _lib.cur_stream()))
+        return True
+
+    def release_workspace(self):
+        self._ws = None
+
+    # ------------------------------------------------------------------ target extraction
+    def _check_image(self, image):
+        if image.dim() != 4 or image.shape[0] != 1 or image.shape[1] != 3:
+            raise ValueError(f'expected a [1,3,H,W] image, got {tuple(image.shape)}')
+        return image.detach().to(self.device, torch.float32).contiguous()
+
+    def style_stats(self, image):
+        image = self._check_image(image)
+        _, _, h, w = image.shape
+        means = [torch.empty(c, device=self.device) for c in STYLE_CHANNELS]
+        srms = [torch.empty(c, c, device=self.device) for c in STYLE_CHANNELS]
+        mp, _k1 = _lib.ptr_array(means)
+        sp, _k2 = _lib.ptr_array(srms)
+        _lib.check(self.lib.stb_style_stats(self.ctx, _lib.ptr(image), h, w, mp, sp, _lib.cur_stream()))
+        return means, srms
+
+    def content_features(self, image):
+        image = self._check_image(image)
+        _, _, h, w = image.shape
+        out = torch.empty(h // 8, w // 8, 512, dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.stb_content_features(self.ctx, _lib.ptr(image), h, w, _lib.ptr(out), _lib.cur_stream()))
+        return out
+
+    def set_targets(self, h, w, content_target, content_weight, means, srms, layer_weights, tv_weight, eps=1e-4):
+        mp, _k1 = _lib.ptr_array(means)
+        sp, _k2 = _lib.ptr_array(srms)
+        lw = (ctypes.c_float * 5)(*layer_weights)
+        _lib.check(self.lib.stb_set_targets(self.ctx, h, w, _lib.ptr(content_target), content_weight, mp, sp, lw,
+                                            tv_weight, eps, _lib.cur_stream()))
+
+
+class StyleTransfer:
+    def __init__(self, devices=['cpu'], pooling='max', *, vgg_weights=None):
+        self.devices = [torch.device(device) for device in devices]
+        self.image = None
+        self.average = None
+
+        self.content_layers = [22]
+        self.style_layers = [1, 6, 11, 20, 29]
+        raw = [256, 64, 16, 4, 1]
+        total = sum(abs(w) for w in raw)
+        self.style_weights = [w / total for w in raw]
+
+        if len(self.devices) not in (1, 2):
+            raise ValueError('Only 1 or 2 devices are supported.')
+        if any(d.type != 'cuda' for d in self.devices):
+            raise RuntimeError('style-transfer-pytorch_b200 runs its hot path only on CUDA (sm_100a) devices; '
+                               f'got devices={[str(d) for d in self.devices]}. There is no CPU fallback.')
+        if not torch.cuda.is_available():
+            raise RuntimeError('CUDA is not available; the B200-native hot path cannot run.')
+        if len(self.devices) == 2:
+            warnings.warn('the reference\'s 2-device layer split (ST:326-333) is superseded; running on '
+                          f'{self.devices[0]} only')
+        dev = self.devices[0]
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        self._dev = dev
+        if vgg_weights is None:
+            vgg_weights = load_vgg19_conv_weights()
+        self.model = NativeVGG(vgg_weights, pooling, dev)
+        self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.last_loss_terms = None
+
+    # ------------------------------------------------------------------ results
+    def get_image_tensor(self):
+        return self.average.get().detach()[0].clamp(0, 1)
+
+    def get_image(self, image_type='pil'):
+        if self.average is None:
+            return None
+        image = self.get_image_tensor()
+        kind = image_type.lower()
+        if kind == 'pil':
+            arr = image.mul(255).byte().permute(1, 2, 0).cpu().numpy()  # torchvision to_pil_image semantics
+            return Image.fromarray(arr)
+        if kind == 'np_uint16':
+            return np.uint16(np.round(image.cpu().movedim(0, 2).numpy() * 65535))
+        raise ValueError("image_type must be 'pil' or 'np_uint16'")
+
+    # ------------------------------------------------------------------ helpers
+    def _initial_image(self, init, content_image, style_images, style_weights, cw, ch):
+        if init == 'content':
+            return _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC))
+        if init == 'gray':
+            return torch.rand([1, 3, ch, cw]) / 255 + 0.5
+        if init == 'uniform':
+            return torch.rand([1, 3, ch, cw])
+        if init == 'normal':
+            image = torch.empty([1, 3, ch, cw])
+            torch.nn.init.trunc_normal_(image, mean=0.5, std=0.25, a=0, b=1)
+            return image
+        if init == 'style_stats':
+            means, variances = 0, 0
+            for weight, simg in zip(style_weights, style_images):
+                t = _pil_to_tensor(simg)[0]
+                means = means + t.mean(dim=(1, 2)) * weight
+                variances = variances + t.var(dim=(1, 2)) * weight
+            planes = []
+            for mean, variance in zip(means, variances):
+                plane = torch.empty([1, 1, ch, cw])
+                torch.nn.init.trunc_normal_(plane, mean=mean, std=variance.sqrt(), a=0, b=1)
+                planes.append(plane)
+            return torch.cat(planes, dim=1)
+        raise ValueError("init must be one of 'content', 'gray', 'uniform', 'style_mean'")
+
+    def _iterate(self, exp_avg, exp_avg_sq, step, lr, avg_decay, want_loss):
+        m = self.model
+        _lib.check(m.lib.stb_iterate(m.ctx, _lib.ptr(self.image), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                     _lib.ptr(self.average.value), step, lr, 0.9, 0.99, 1e-8, avg_decay,
+                                     _lib.ptr(self._loss_host) if want_loss else None, _lib.cur_stream()))
+        self.average.note_update()
+
+    def loss_and_grad(self):
+        """Closure of ST:472-476 evaluated natively on the current image: returns (terms[8] host tensor, grad)."""
+        m = self.model
+        grad = torch.empty_like(self.image)
+        _lib.check(m.lib.stb_iterate_ex(m.ctx, _lib.ptr(self.image), None, None, None, 0, 0.0, 0.9, 0.99, 1e-8, 0.0, 0,
+                                        _lib.ptr(grad), _lib.ptr(self._loss_host), _lib.cur_stream()))
+        torch.cuda.current_stream().synchronize()
+        return self._loss_host.clone(), grad
+
+    # ------------------------------------------------------------------ the driver
+    def stylize(self, content_image, style_images, *,
+                style_weights=None,
+                content_weight: float = 0.015,
+                tv_weight: float = 2.,
+                optimizer: str = 'adam',
+                min_scale: int = 128,
+                end_scale: int = 512,
+                iterations: int = 500,
+                initial_iterations: int = 1000,
+                step_size: float = 0.02,
+                avg_decay: float = 0.99,
+                init: str = 'content',
+                style_scale_fac: float = 1.,
+                style_size: int = None,
+                callback=None):
+        dev = self._dev
+        min_scale = min(min_scale, end_scale)
+        if style_weights is None:
+            style_weights = [1 / len(style_images)] * len(style_images)
+        else:
+            norm = sum(abs(w) for w in style_weights)
+            style_weights = [w / norm for w in style_weights]
+        if len(style_images) != len(style_weights):
+            raise ValueError('style_images and style_weights must have the same length')
+        if optimizer not in ('adam', 'lbfgs'):
+            raise ValueError("optimizer must be one of 'adam', 'lbfgs'")
+        per_content_weight = content_weight / len(self.content_layers)
+
+        scales = gen_scales(min_scale, end_scale)
+        cw, ch = size_to_fit(content_image.size, scales[0], scale_up=True)
+        self.image = self._initial_image(init, content_image, style_images, style_weights, cw, ch).to(dev)
+
+        exp_avg = exp_avg_sq = None
+        step = 0
+        lbfgs = None
+        with torch.cuda.device(dev), torch.no_grad():
+            for scale in scales:
+                self.model.release_workspace()
+                torch.cuda.empty_cache()
+
+                cw, ch = size_to_fit(content_image.size, scale, scale_up=True)
+                content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC)).to(dev)
+                styles = []
+                for simg in style_images:
+                    if style_size is None:
+                        sw, sh = size_to_fit(simg.size, round(scale * style_scale_fac))
+                    else:
+                        sw, sh = size_to_fit(simg.size, style_size)
+                    styles.append((sw, sh, _pil_to_tensor(simg.resize((sw, sh), Image.BICUBIC)).to(dev)))
+                self.model.ensure_workspace([(ch, cw)] + [(sh, sw) for sw, sh, _ in styles])
+
+                self.image = _resize(self.image.detach(), (ch, cw), 'bicubic').clamp_(0, 1).contiguous()
+                self.average = EMA(self.image, avg_decay)
+
+                print(f'Processing content image ({cw}x{ch})...')
+                content_target = self.model.content_features(content)
+                means = srms = None
+                for weight, (sw, sh, simg) in zip(style_weights, styles):
+                    print(f'Processing style image ({sw}x{sh})...')
+                    m_i, s_i = self.model.style_stats(simg)
+                    if means is None:
+                        means = [m * weight for m in m_i]
+                        srms = [s * weight for s in s_i]
+                    else:
+                        for acc, m in zip(means, m_i):
+                            acc.add_(m * weight)
+                        for acc, s in zip(srms, s_i):
+                            acc.add_(s * weight)
+                self.model.set_targets(ch, cw, content_target, per_content_weight, means, srms, self.style_weights,
+                                       tv_weight)
+
+                if optimizer == 'adam':
+                    if exp_avg is None:
+                        exp_avg = torch.zeros_like(self.image)
+                        exp_avg_sq = torch.zeros_like(self.image)
+                    else:  # warm start at the new size, step counter carried over (ST:285-295, 460-462)
+                        exp_avg = _resize(exp_avg, (ch, cw), 'bicubic').contiguous()
+                        exp_avg_sq = _resize(exp_avg_sq, (ch, cw), 'bilinear').relu_().contiguous()
+                else:
+                    lbfgs = self._make_lbfgs()
+                torch.cuda.empty_cache()
+
+                actual_its = initial_iterations if scale == scales[0] else iterations
+                for i in range(1, actual_its + 1):
+                    if optimizer == 'adam':
+                        step += 1
+                        self._iterate(exp_avg, exp_avg_sq, step, step_size, avg_decay, callback is not None)
+                    else:
+                        loss_value = self._lbfgs_step(lbfgs, avg_decay)
+                    if callback is not None:
+                        if optimizer == 'adam':
+                            torch.cuda.current_stream().synchronize()
+                            self.last_loss_terms = self._loss_host.clone()
+                            loss_value = float(self._loss_host[0])
+                        gpu_ram = 0
+                        for device in self.devices:
+                            if device.type == 'cuda':
+                                gpu_ram = max(gpu_ram, torch.cuda.max_memory_allocated(device))
+                        callback(STIterate(w=cw, h=ch, i=i, i_max=actual_its, loss=loss_value, time=time.time(),
+                                           gpu_ram=gpu_ram))
+
+                self.image.copy_(self.average.get())
+
+        return self.get_image()
+
+    # ------------------------------------------------------------------ L-BFGS (ST:464-465): torch's optimizer on the
+    # host, closure evaluated by the native library
+    def _make_lbfgs(self):
+        self._lbfgs_param = torch.nn.Parameter(self.image, requires_grad=True)
+        return torch.optim.LBFGS([self._lbfgs_param], max_iter=1, history_size=10)
+
+    def _lbfgs_step(self, opt, avg_decay):
+        def closure():
+            terms, grad = self.loss_and_grad()
+            self._lbfgs_param.grad = grad
+            return terms[0].to(self._dev)
+
+        with torch.enable_grad():
+            loss = opt.step(closure)
+        self.average.value.mul_(avg_decay).add_(self.image, alpha=1 - avg_decay)
+        self.average.note_update()
+        return float(loss)

@@ -1,0 +1,73 @@
+"""Pins oracle/st_oracle.py against golden vectors produced by the unmodified reference (tests/golden/make_golden.py).
+
+Tolerances: the reference itself is fp32 and its W2 loss is a cancellation, so two correct fp32 evaluations differ
+by ~1e-5 relative on the loss; after a few Adam steps (sign-like updates, lr 0.02) single pixels may differ more.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import st_oracle as O
+
+GOLD = Path(__file__).resolve().parent / 'golden'
+import importlib.util
+_spec = importlib.util.spec_from_file_location('make_golden', GOLD / 'make_golden.py')
+MG = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(MG)
+
+
+@pytest.mark.parametrize('name', list(MG.CASES))
+def test_stylize_trace_matches_reference(name, vgg_weights):
+    gold = np.load(GOLD / f'{name}.npz')
+    content, styles, pooling, kw = MG.build_case(name)
+    trace = []
+    out = O.stylize(content, styles, vgg_weights, pooling=pooling,
+                    callback=lambda si, i, loss, st: trace.append((loss, st.image.shape[3], st.image.shape[2], i)), **kw)
+    losses = np.array([t[0] for t in trace])
+    assert len(losses) == len(gold['losses'])
+    np.testing.assert_array_equal(np.array([(t[1], t[2], t[3]) for t in trace]), gold['sizes'][:, :3])
+    np.testing.assert_allclose(losses, gold['losses'], rtol=2e-4)
+    diff = np.abs(out.numpy() - gold['final_image'])
+    assert diff.mean() < 2e-4 and np.quantile(diff, 0.999) < 2e-2
+
+
+def test_single_iteration_terms_and_gradient(vgg_weights):
+    gold = np.load(GOLD / 'max_64x48_internals.npz')
+    content, styles, pooling, _ = MG.build_case('max_64x48_single')
+    tg, (cw, ch) = O.make_targets(content, styles, [1.0], 64, vgg_weights, pooling, 0.015, 2.0)
+    img = torch.from_numpy(gold['image'])
+    detail = {}
+    loss, grad = O.loss_and_grad(img, vgg_weights, tg, pooling, detail=detail)
+    np.testing.assert_allclose(detail['terms'], gold['terms'], rtol=3e-4)
+    np.testing.assert_allclose(float(loss), float(gold['total']), rtol=1e-4)
+    g, gr = grad.numpy(), gold['grad']
+    assert np.linalg.norm(g - gr) / np.linalg.norm(gr) < 2e-3
+    np.testing.assert_allclose(detail['acts'][1].numpy()[:, :8], gold['tap1'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(detail['acts'][29].numpy()[:, :8], gold['tap29'], rtol=1e-3, atol=1e-4)
+
+
+def test_fp64_oracle_agrees_with_fp32(vgg_weights):
+    """The restatement in double precision bounds the fp32 noise floor of the loss terms."""
+    gold = np.load(GOLD / 'max_64x48_internals.npz')
+    content, styles, pooling, _ = MG.build_case('max_64x48_single')
+    w64 = [(w.double(), b.double()) for w, b in vgg_weights]
+    tg32, _ = O.make_targets(content, styles, [1.0], 64, vgg_weights, pooling, 0.015, 2.0)
+    tg64 = O.ScaleTargets(tg32.content_target.double(),
+                          [O.StyleTarget.build(s.mean.double(), (s.cov - torch.eye(s.mean.numel()) * 1e-4
+                                                                 + torch.outer(s.mean, s.mean)).double())
+                           for s in tg32.style], 0.015, 2.0)
+    img = torch.from_numpy(gold['image'])
+    l32, _ = O.loss_and_grad(img, vgg_weights, tg32, pooling)
+    l64, _ = O.loss_and_grad(img.double(), w64, tg64, pooling)
+    assert abs(float(l32) - float(l64)) / float(l64) < 1e-3
+
+
+def test_size_helpers():
+    assert O.gen_scales(128, 512) == [128, 181, 256, 362, 512]
+    assert O.gen_scales(128, 2896)[-1] == 2896 and len(O.gen_scales(128, 2896)) == 10
+    assert O.size_to_fit((2896, 2172), 128, scale_up=True) == (128, 96)
+    assert O.size_to_fit((100, 50), 512) == (100, 50)
+    with pytest.raises(ValueError):
+        O.vgg_forward(torch.zeros(1, 3, 15, 40), O.make_vgg_weights(1), 'max', 29)
