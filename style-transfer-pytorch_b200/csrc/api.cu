@@ -111,7 +111,7 @@ void make_plan(const stb_ctx* ctx, int H, int W, Plan* pl) {
   pl->g_off[0] = take(gmax);
   pl->g_off[1] = take(gmax);
   pl->gtv_off = take((size_t)3 * H * W * 4);
-  pl->n_tv_partials = ((W + 63) / 64) * H;
+  pl->n_tv_partials = ((W + 127) / 128) * H;
   pl->tvp_off = take((size_t)pl->n_tv_partials * 4);
   pl->ssep_off = take(1024 * 4);
   size_t gp = 0;

@@ -49,14 +49,15 @@ __device__ float tv_gpad_slow(const float* __restrict__ x, int H, int W, int a, 
   return g;
 }
 
-__global__ void __launch_bounds__(256)
+// block = 128 threads = 4 warps; warp w owns output channels [16w, 16w+16) (weights are warp-uniform smem broadcasts),
+// lane l owns the 4 consecutive pixels x0..x0+3 with x0 = (blockIdx.x*32 + l)*4.  grid: (ceil(W/128), H).
+__global__ void __launch_bounds__(128)
 conv0_fwd_tv_kernel(const float* __restrict__ img, const float* __restrict__ w0, const float* __restrict__ b0,
                     bf16* __restrict__ out, int H, int W, int do_tv, TvConst tc, float* __restrict__ gtv,
                     float* __restrict__ tv_partials) {
   __shared__ __align__(16) float s_w[27 * 64];  // [k = (c*3+ky)*3+kx][co]
   __shared__ float s_b[64];
-  __shared__ float s_red[8];
-  for (int i = threadIdx.x; i < 27 * 64; i += 256) {
+  for (int i = threadIdx.x; i < 27 * 64; i += 128) {
     const int co = i & 63, k = i >> 6;
     s_w[i] = w0[co * 27 + k];
   }
@@ -64,172 +65,224 @@ conv0_fwd_tv_kernel(const float* __restrict__ img, const float* __restrict__ w0,
   __syncthreads();
 
   const int y = blockIdx.y;
-  const int x = blockIdx.x * 64 + (threadIdx.x >> 2);
-  const int cg = threadIdx.x & 3;
+  const int cg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = (blockIdx.x * 32 + lane) * 4;
   float tv_local = 0.f;
-  if (x < W) {
-    float raw[3][3][3];
+  if (x0 < W) {
+    float raw[3][3][6];
     const int ys[3] = {clampi(y - 1, 0, H - 1), y, clampi(y + 1, 0, H - 1)};
-    const int xs[3] = {clampi(x - 1, 0, W - 1), x, clampi(x + 1, 0, W - 1)};
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {
+        const float* row = img + ((size_t)c * H + ys[i]) * W;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) raw[c][i][j] = __ldg(img + ((size_t)c * H + ys[i]) * W + xs[j]);
-
-    float acc[16];
+        for (int j = 0; j < 6; ++j) raw[c][i][j] = __ldg(row + clampi(x0 - 1 + j, 0, W - 1));
+      }
+    float acc[4][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = s_b[cg * 16 + i];
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[p][i] = s_b[cg * 16 + i];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {
+        float nv[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) nv[j] = (raw[c][i][j] - c_mean[c]) / c_std[c];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const float v = (raw[c][i][j] - c_mean[c]) / c_std[c];
           const float4* wp = reinterpret_cast<const float4*>(&s_w[((c * 3 + i) * 3 + j) * 64 + cg * 16]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 wv = wp[q];
-            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[p][4 * q + 0] = fmaf(nv[p + j], wv.x, acc[p][4 * q + 0]);
+              acc[p][4 * q + 1] = fmaf(nv[p + j], wv.y, acc[p][4 * q + 1]);
+              acc[p][4 * q + 2] = fmaf(nv[p + j], wv.z, acc[p][4 * q + 2]);
+              acc[p][4 * q + 3] = fmaf(nv[p + j], wv.w, acc[p][4 * q + 3]);
+            }
           }
         }
-    uint32_t pk[8];
+      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
-    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * W + x) * 64 + cg * 16);
-    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + p < W) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(fmaxf(acc[p][2 * i], 0.f), fmaxf(acc[p][2 * i + 1], 0.f));
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * W + x0 + p) * 64 + cg * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
 
-    if (do_tv && cg < 3) {
-      // channel cg of this pixel: TV loss share + gradient (fast path from the 3x3 raw neighbourhood)
-      const int c = cg;
-      const float(*n)[3] = raw[c];
-      const float ctr = n[1][1];
-      const bool hasL = x > 0, hasR = x < W - 1, hasU = y > 0, hasD = y < H - 1;
-      // owned loss entries: e1[y][x], e2[y][x], e3[y][x], e4[y][x] (+ the extra row i=H / col j=W at the far borders)
-      const float e1 = n[1][2] - ctr, e2 = n[2][1] - ctr;
-      // e3[i][j] = X[c(i)][c(j)] - X[c(i-1)][c(j-1)] at (i,j)=(y,x):  ctr - n[0][0]
-      const float e3 = ctr - n[0][0];
-      // e4[i][j] = X[c(i)][c(j-1)] - X[c(i-1)][c(j)] at (y,x): n[1][0] - n[0][1]
-      const float e4 = n[1][0] - n[0][1];
-      float l = tc.l1 * (e1 * e1 + e2 * e2) + tc.l3 * (e3 * e3 + e4 * e4);
-      if (!hasD) {  // row i = H: X[H-1][c(j)] - X[H-1][c(j-1)]  and  X[H-1][c(j-1)] - X[H-1][c(j)]
-        const float d = ctr - n[1][0];
-        l += tc.l3 * (d * d + d * d);
+    if (do_tv && cg == 0) {  // warp-uniform: warp 0 also owns the TV loss / gradient of its 4 pixels x 3 channels
+      const bool hasU = y > 0, hasD = y < H - 1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float gout[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int x = x0 + p;
+          gout[p] = 0.f;
+          if (x < W) {
+            // n[i][j] = raw[c][i][p + j]
+            const float ctr = raw[c][1][p + 1];
+            const float nL = raw[c][1][p], nR = raw[c][1][p + 2], nU = raw[c][0][p + 1], nDn = raw[c][2][p + 1];
+            const float nUL = raw[c][0][p], nUR = raw[c][0][p + 2], nDL = raw[c][2][p], nDR = raw[c][2][p + 2];
+            const bool hasL = x > 0, hasR = x < W - 1;
+            const float e1 = nR - ctr, e2 = nDn - ctr, e3 = ctr - nUL, e4 = nL - nU;
+            float l = tc.l1 * (e1 * e1 + e2 * e2) + tc.l3 * (e3 * e3 + e4 * e4);
+            if (!hasD) { const float d = ctr - nL; l += tc.l3 * (d * d + d * d); }   // extra row i = H
+            if (!hasR) { const float d = ctr - nU; l += tc.l3 * (d * d + d * d); }   // extra col j = W
+            tv_local += l;
+            float g;
+            if (hasL && hasR && hasU && hasD) {
+              g = tc.k1 * (4.f * ctr - nL - nR - nU - nDn) + tc.k3 * (4.f * ctr - nUL - nDR - nUR - nDL);
+            } else {
+              const float* plane = img + (size_t)c * H * W;
+              g = 0.f;
+              for (int a = (hasU ? y + 1 : 0); a <= (hasD ? y + 1 : H + 1); ++a)
+                for (int b = (hasL ? x + 1 : 0); b <= (hasR ? x + 1 : W + 1); ++b)
+                  g += tv_gpad_slow(plane, H, W, a, b, tc.k1, tc.k3);
+            }
+            gout[p] = g;
+          }
+        }
+        float* gp = gtv + ((size_t)c * H + y) * W + x0;
+        if ((W & 3) == 0) {
+          *reinterpret_cast<float4*>(gp) = make_float4(gout[0], gout[1], gout[2], gout[3]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (x0 + p < W) gp[p] = gout[p];
+        }
       }
-      if (!hasR) {  // col j = W: X[c(i)][W-1] - X[c(i-1)][W-1]  and  X[c(i)][W-1] - X[c(i-1)][W-1] (e4 sign flipped)
-        const float d = ctr - n[0][1];
-        l += tc.l3 * (d * d + d * d);
-      }
-      // corner entry (i=H, j=W) is identically zero
-      tv_local = l;
-      float g;
-      if (hasL && hasR && hasU && hasD) {
-        g = tc.k1 * (4.f * ctr - n[1][0] - n[1][2] - n[0][1] - n[2][1]) +
-            tc.k3 * (4.f * ctr - n[0][0] - n[2][2] - n[0][2] - n[2][0]);
-      } else {
-        const float* plane = img + (size_t)c * H * W;
-        g = 0.f;
-        for (int a = (hasU ? y + 1 : 0); a <= (hasD ? y + 1 : H + 1); ++a)
-          for (int b = (hasL ? x + 1 : 0); b <= (hasR ? x + 1 : W + 1); ++b)
-            g += tv_gpad_slow(plane, H, W, a, b, tc.k1, tc.k3);
-      }
-      gtv[((size_t)c * H + y) * W + x] = g;
     }
   }
-  if (do_tv) {
-    float s = warp_sum(tv_local);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int i = 0; i < 8; ++i) t += s_red[i];
-      tv_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
-    }
+  if (do_tv && cg == 0) {
+    const float sum = warp_sum(tv_local);
+    if (lane == 0) tv_partials[blockIdx.y * gridDim.x + blockIdx.x] = sum;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ conv0 bwd + Adam
-// 8 lanes per pixel (8 channels of g0 each); a warp covers 4 consecutive pixels of a row.
-__device__ __forceinline__ void conv0_gpad(const bf16* __restrict__ g0, const float* __restrict__ s_w, int H, int W,
-                                           int a, int b, int sub, float (&acc)[3]) {
-  // gradient on the replicate-padded grid position (a,b): sum over taps of g0[a-ky][b-kx][:] . W[:, c, ky, kx]
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yo = a - ky;
-    if (yo < 0 || yo >= H) continue;
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xo = b - kx;
-      if (xo < 0 || xo >= W) continue;
-      const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g0 + ((size_t)yo * W + xo) * 64 + sub * 8));
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-      float gf[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { gf[2 * i] = bf16lo(gw[i]); gf[2 * i + 1] = bf16hi(gw[i]); }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float4* wp = reinterpret_cast<const float4*>(&s_w[((ky * 3 + kx) * 3 + c) * 64 + sub * 8]);
-        const float4 w0 = wp[0], w1 = wp[1];
-        acc[c] = fmaf(gf[0], w0.x, acc[c]); acc[c] = fmaf(gf[1], w0.y, acc[c]);
-        acc[c] = fmaf(gf[2], w0.z, acc[c]); acc[c] = fmaf(gf[3], w0.w, acc[c]);
-        acc[c] = fmaf(gf[4], w1.x, acc[c]); acc[c] = fmaf(gf[5], w1.y, acc[c]);
-        acc[c] = fmaf(gf[6], w1.z, acc[c]); acc[c] = fmaf(gf[7], w1.w, acc[c]);
-      }
-    }
-  }
-}
+// One warp = a strip of 32 consecutive pixels of one row.  Lanes are CHANNELS (lane l owns g0 channels 2l, 2l+1 and
+// keeps their 2 x 27 weights in registers); the strip is walked pixel by pixel with a sliding 3x3 window of
+// coalesced 128-byte loads (3 new loads per step), the three image-channel sums are butterfly-reduced and parked
+// on lane p; afterwards lane p applies Normalize-backward + TV gradient + Adam + clamp + EMA to pixel p (coalesced).
+struct F2 { float x, y; };
 
 __global__ void __launch_bounds__(256)
 conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const float* __restrict__ w0, const float* __restrict__ gtv,
                       float* __restrict__ img, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                       float* __restrict__ ema, float* __restrict__ grad_out, int H, int W, AdamScalars ac,
                       int apply_update) {
-  __shared__ __align__(16) float s_w[27 * 64];  // [(ky*3+kx)*3 + c][co]
-  for (int i = threadIdx.x; i < 27 * 64; i += 256) {
-    const int co = i & 63, k = i >> 6;
-    const int c = k % 3, tap = k / 3;
-    s_w[i] = w0[(co * 3 + c) * 9 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, sub = lane & 7;
-  const long gp = ((long)blockIdx.x * 256 + threadIdx.x) >> 3;  // global pixel id
-  const long total = (long)H * W;
-  const bool valid = gp < total;
-  const int y = valid ? (int)(gp / W) : 0, x = valid ? (int)(gp % W) : 0;
-  float acc[3] = {0.f, 0.f, 0.f};
-  if (valid) {
-    const int a0 = (y == 0) ? 0 : y + 1, a1 = (y == H - 1) ? H + 1 : y + 1;
-    const int b0 = (x == 0) ? 0 : x + 1, b1 = (x == W - 1) ? W + 1 : x + 1;
-    for (int a = a0; a <= a1; ++a)
-      for (int b = b0; b <= b1; ++b) conv0_gpad(g0, s_w, H, W, a, b, sub, acc);
-  }
+  const int lane = threadIdx.x & 31;
+  const int strips = (W + 31) >> 5;
+  const long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wg >= (long)H * strips) return;
+  const int y = (int)(wg / strips);
+  const int xs = (int)(wg % strips) * 32;
+  const uint32_t* __restrict__ g32 = reinterpret_cast<const uint32_t*>(g0);
+
+  // wr[tap][c]: weights of this lane's two channels; tap = ky*3+kx
+  F2 wr[9][3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      wr[t][c].x = __ldg(w0 + ((2 * lane) * 3 + c) * 9 + t);
+      wr[t][c].y = __ldg(w0 + ((2 * lane + 1) * 3 + c) * 9 + t);
+    }
+
+  auto ld = [&](int yo, int xo) -> F2 {
+    F2 r{0.f, 0.f};
+    if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
+      const uint32_t u = __ldg(g32 + ((size_t)yo * W + xo) * 32 + lane);
+      r.x = bf16lo(u);
+      r.y = bf16hi(u);
+    }
+    return r;
+  };
+
+  float keep[3] = {0.f, 0.f, 0.f};
+  F2 win[3][3];
+  bool have = false;
+  const bool row_interior = (y > 0) && (y < H - 1);
+  const int xe = min(xs + 32, W);
+  for (int x = xs; x < xe; ++x) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    if (row_interior && x > 0 && x < W - 1) {
+      if (have) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { win[r][0] = win[r][1]; win[r][1] = win[r][2]; win[r][2] = ld(y - 1 + r, x + 1); }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cidx = 0; cidx < 3; ++cidx) win[r][cidx] = ld(y - 1 + r, x - 1 + cidx);
+        have = true;
+      }
+      // padded position (y+1, x+1): g0[y+1-ky][x+1-kx] <-> win[2-ky][2-kx]
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cidx = 0; cidx < 3; ++cidx) {
+          const int t = (2 - r) * 3 + (2 - cidx);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            acc[c] = fmaf(win[r][cidx].x, wr[t][c].x, acc[c]);
+            acc[c] = fmaf(win[r][cidx].y, wr[t][c].y, acc[c]);
+          }
+        }
+    } else {
+      // border pixel: sum over the padded positions that replicate-padding folds onto it (warp-uniform branch)
+      have = false;
+      const int a0 = (y == 0) ? 0 : y + 1, a1 = (y == H - 1) ? H + 1 : y + 1;
+      const int b0 = (x == 0) ? 0 : x + 1, b1 = (x == W - 1) ? W + 1 : x + 1;
+      for (int a = a0; a <= a1; ++a)
+        for (int b = b0; b <= b1; ++b)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const F2 v = ld(a - ky, b - kx);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                acc[c] = fmaf(v.x, wr[ky * 3 + kx][c].x, acc[c]);
+                acc[c] = fmaf(v.y, wr[ky * 3 + kx][c].y, acc[c]);
+              }
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (lane == x - xs) { keep[0] = acc[0]; keep[1] = acc[1]; keep[2] = acc[2]; }
   }
-  if (valid && sub < 3) {
-    const int c = sub;
-    const size_t idx = ((size_t)c * H + y) * W + x;
-    const float gsel = (c == 0) ? acc[0] : ((c == 1) ? acc[1] : acc[2]);
-    const float g = gsel / c_std[c] + (gtv ? gtv[idx] : 0.f);
-    if (grad_out) grad_out[idx] = g;
-    if (apply_update) {
-      float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
-      m = m + (g - m) * ac.one_minus_b1;
-      v = v * ac.b2 + ac.one_minus_b2 * g * g;
-      const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
-      p = p - ac.step_size * (m / denom);
-      p = fminf(fmaxf(p, 0.f), 1.f);
-      e = e * ac.ema_decay + ac.one_minus_decay * p;
-      exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+
+  const int x = xs + lane;
+  if (x < W) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t idx = ((size_t)c * H + y) * W + x;
+      const float g = keep[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
+      if (grad_out) grad_out[idx] = g;
+      if (apply_update) {
+        float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
+        m = m + (g - m) * ac.one_minus_b1;
+        v = v * ac.b2 + ac.one_minus_b2 * g * g;
+        const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
+        p = p - ac.step_size * (m / denom);
+        p = fminf(fmaxf(p, 0.f), 1.f);
+        e = e * ac.ema_decay + ac.one_minus_decay * p;
+        exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+      }
     }
   }
 }
@@ -383,7 +436,7 @@ sse_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long n8, floa
 // ================================================================================================ launchers
 int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* out, int H, int W, float tv_weight,
                      float* gtv, float* tv_partials, int* n_partials, cudaStream_t s) {
-  dim3 grid((W + 63) / 64, H);
+  dim3 grid((W + 127) / 128, H);
   TvConst tc{};
   const int do_tv = gtv != nullptr;
   if (do_tv) {
@@ -394,7 +447,7 @@ int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* o
     tc.l3 = (float)(2.0 / (12.0 * n3));
   }
   if (n_partials) *n_partials = grid.x * grid.y;
-  conv0_fwd_tv_kernel<<<grid, 256, 0, s>>>(img, w0, b0, out, H, W, do_tv, tc, gtv, tv_partials);
+  conv0_fwd_tv_kernel<<<grid, 128, 0, s>>>(img, w0, b0, out, H, W, do_tv, tc, gtv, tv_partials);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
@@ -402,8 +455,8 @@ int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* o
 int launch_conv0_bwd_adam(const bf16* g0, const float* w0, const float* gtv, float* img, float* exp_avg,
                           float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars& a,
                           int apply_update, cudaStream_t s) {
-  const long threads = (long)H * W * 8;
-  const int blocks = (int)((threads + 255) / 256);
+  const long warps = (long)H * ((W + 31) / 32);
+  const int blocks = (int)((warps + 7) / 8);
   conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a,
                                                apply_update);
   STB_CUDA_CHECK(cudaGetLastError());

@@ -66,6 +66,7 @@ int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, 
 struct GemmProb {  // D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I, all n x n row-major fp32
   const float *A, *B, *A2, *B2, *Cadd;
   float* D;
+  float* red_out;  // optional: per-tile {sum of squares, trace} of D, [ (n/64)^2 ][2]
   int n, transA, transB, transA2, transB2;
   float alpha, alpha2, beta, gamma;
 };
@@ -83,6 +84,7 @@ struct W2Layer {
   float* gmu_bias;  // out: (d loss / d mean) / npix              -> per-channel bias of the tap-gradient GEMM
   bf16* gs_bf16;    // out: (G + G^T) / npix as bf16 [n][n]       -> B operand of the tap-gradient GEMM
   float* scal;      // W2S_* scalars
+  float* red;       // reduction partials {sum of squares, trace} x 64
 };
 struct W2Round { int first_tile, n_tiles; };
 struct W2Engine {

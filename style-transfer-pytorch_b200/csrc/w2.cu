@@ -16,189 +16,271 @@ namespace stb {
 
 namespace {
 
-constexpr int TS = 64;   // tile size
-constexpr int KS = 16;   // k step
+constexpr int TS = 64;     // output tile
+constexpr int KC = 8;      // k chunk per smem stage
+constexpr int KG = 8;      // in-CTA split-K groups (64 threads each) -> 512 threads
+constexpr int NRED = 64;   // max reduction partials per layer (tiles of a 512x512 problem / helper CTAs)
 
-__global__ void __launch_bounds__(256)
+// D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I on 64x64 tiles.  One CTA = 8 k-groups x 64
+// threads; a group owns 1/8 of K with private smem double buffers and 8x8 register tiles (FMA:LDS = 16:1), the
+// groups' partial tiles are tree-reduced through smem, group 0 applies the epilogue.  Optionally writes the tile's
+// {sum of squares, trace} partial for the Frobenius norms of the Newton-Schulz chain (deterministic order).
+__global__ void __launch_bounds__(KG * 64, 1)
 sgemm_grouped_kernel(const GemmProb* __restrict__ probs, const uint32_t* __restrict__ tiles) {
-  __shared__ __align__(16) float As[2][KS][TS + 4];
-  __shared__ __align__(16) float Bs[2][KS][TS + 4];
+  extern __shared__ __align__(16) float smem_f[];
   const uint32_t t = tiles[blockIdx.x];
   const GemmProb pr = probs[t >> 16];
   const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
   const int n = pr.n;
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  const int grp = threadIdx.x >> 6, lt = threadIdx.x & 63;
+  const int tx = lt & 7, ty = lt >> 3;
+  float* As = smem_f + grp * (4 * KC * TS);  // [2][KC][TS]
+  float* Bs = As + 2 * KC * TS;              // [2][KC][TS]
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+  const int kper = n / KG;           // k range of this group (n is a multiple of 64)
+  const int kbeg = grp * kper;
   const int n_prod = (pr.A2 != nullptr) ? 2 : 1;
   for (int pi = 0; pi < n_prod; ++pi) {
     const float* __restrict__ A = pi ? pr.A2 : pr.A;
     const float* __restrict__ B = pi ? pr.B2 : pr.B;
     const int tA = pi ? pr.transA2 : pr.transA, tB = pi ? pr.transB2 : pr.transB;
     const float alpha = pi ? pr.alpha2 : pr.alpha;
-    float4 ra, rb;
+    float4 ra[2], rb[2];
     auto gload = [&](int k0) {
-      if (!tA) {  // A[i][k]: thread -> row i = tid & 63, k quad = tid >> 6
-        ra = *reinterpret_cast<const float4*>(A + (size_t)(ti * TS + (tid & 63)) * n + k0 + (tid >> 6) * 4);
-      } else {    // A^T: element (i,k) = A[k][i]: thread -> k = tid >> 4, i quad = tid & 15
-        ra = *reinterpret_cast<const float4*>(A + (size_t)(k0 + (tid >> 4)) * n + ti * TS + (tid & 15) * 4);
+      if (!tA) {  // A[i][k]: thread = row i, 8 consecutive k
+        const float4* p = reinterpret_cast<const float4*>(A + (size_t)(ti * TS + lt) * n + k0);
+        ra[0] = p[0]; ra[1] = p[1];
+      } else {    // A^T(i,k) = A[k][i]: thread = (k = lt>>3, 8 consecutive i)
+        const float4* p = reinterpret_cast<const float4*>(A + (size_t)(k0 + (lt >> 3)) * n + ti * TS + (lt & 7) * 8);
+        ra[0] = p[0]; ra[1] = p[1];
       }
       if (!tB) {  // B[k][j]
-        rb = *reinterpret_cast<const float4*>(B + (size_t)(k0 + (tid >> 4)) * n + tj * TS + (tid & 15) * 4);
-      } else {    // B^T: element (k,j) = B[j][k]
-        rb = *reinterpret_cast<const float4*>(B + (size_t)(tj * TS + (tid & 63)) * n + k0 + (tid >> 6) * 4);
+        const float4* p = reinterpret_cast<const float4*>(B + (size_t)(k0 + (lt >> 3)) * n + tj * TS + (lt & 7) * 8);
+        rb[0] = p[0]; rb[1] = p[1];
+      } else {    // B^T(k,j) = B[j][k]
+        const float4* p = reinterpret_cast<const float4*>(B + (size_t)(tj * TS + lt) * n + k0);
+        rb[0] = p[0]; rb[1] = p[1];
       }
     };
     auto sstore = [&](int buf) {
+      float* a = As + buf * KC * TS;
+      float* b = Bs + buf * KC * TS;
+      const float av[8] = {ra[0].x * alpha, ra[0].y * alpha, ra[0].z * alpha, ra[0].w * alpha,
+                           ra[1].x * alpha, ra[1].y * alpha, ra[1].z * alpha, ra[1].w * alpha};
+      const float bv[8] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w, rb[1].x, rb[1].y, rb[1].z, rb[1].w};
       if (!tA) {
-        const int i = tid & 63, kq = (tid >> 6) * 4;
-        As[buf][kq + 0][i] = ra.x * alpha; As[buf][kq + 1][i] = ra.y * alpha;
-        As[buf][kq + 2][i] = ra.z * alpha; As[buf][kq + 3][i] = ra.w * alpha;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k * TS + lt] = av[k];
       } else {
-        *reinterpret_cast<float4*>(&As[buf][tid >> 4][(tid & 15) * 4]) =
-            make_float4(ra.x * alpha, ra.y * alpha, ra.z * alpha, ra.w * alpha);
+        float4* d = reinterpret_cast<float4*>(a + (lt >> 3) * TS + (lt & 7) * 8);
+        d[0] = make_float4(av[0], av[1], av[2], av[3]);
+        d[1] = make_float4(av[4], av[5], av[6], av[7]);
       }
       if (!tB) {
-        *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = rb;
+        float4* d = reinterpret_cast<float4*>(b + (lt >> 3) * TS + (lt & 7) * 8);
+        d[0] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        d[1] = make_float4(bv[4], bv[5], bv[6], bv[7]);
       } else {
-        const int j = tid & 63, kq = (tid >> 6) * 4;
-        Bs[buf][kq + 0][j] = rb.x; Bs[buf][kq + 1][j] = rb.y; Bs[buf][kq + 2][j] = rb.z; Bs[buf][kq + 3][j] = rb.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[k * TS + lt] = bv[k];
       }
     };
-    gload(0);
+    gload(kbeg);
     sstore(0);
-    __syncthreads();
+    named_bar_sync(1 + grp, 64);
     int buf = 0;
-    for (int k0 = 0; k0 < n; k0 += KS) {
-      const bool more = (k0 + KS) < n;
-      if (more) gload(k0 + KS);
+    for (int k0 = 0; k0 < kper; k0 += KC) {
+      const bool more = (k0 + KC) < kper;
+      if (more) gload(kbeg + k0 + KC);
+      const float* a = As + buf * KC * TS;
+      const float* b = Bs + buf * KC * TS;
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      for (int k = 0; k < KC; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + k * TS + ty * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(a + k * TS + ty * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(b + k * TS + tx * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + k * TS + tx * 8 + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
       if (more) sstore(buf ^ 1);
-      __syncthreads();
+      named_bar_sync(1 + grp, 64);
       buf ^= 1;
     }
   }
+  // ---- tree reduction of the 8 partial tiles through smem (reuses the staging buffers: 8 x 16 KiB)
+  __syncthreads();
+  float* red = smem_f;  // [4][64 threads][64] floats max
+  for (int half = KG / 2; half >= 1; half >>= 1) {
+    if (grp >= half && grp < 2 * half) {
+      float* dst = red + ((grp - half) * 64 + lt) * 64;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gi = ti * TS + ty * 4 + i;
-    const int gj = tj * TS + tx * 4;
-    float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if (pr.Cadd != nullptr) {
-      const float4 c = *reinterpret_cast<const float4*>(pr.Cadd + (size_t)gi * n + gj);
-      o.x = fmaf(pr.beta, c.x, o.x); o.y = fmaf(pr.beta, c.y, o.y);
-      o.z = fmaf(pr.beta, c.z, o.z); o.w = fmaf(pr.beta, c.w, o.w);
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; j += 4)
+          *reinterpret_cast<float4*>(dst + ((i * 8 + j) ^ ((lt & 7) * 4))) =
+              make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
     }
-    if (gi >= gj && gi < gj + 4) (&o.x)[gi - gj] += pr.gamma;
-    *reinterpret_cast<float4*>(pr.D + (size_t)gi * n + gj) = o;
+    __syncthreads();
+    if (grp < half) {
+      const float* src = red + (grp * 64 + lt) * 64;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((i * 8 + j) ^ ((lt & 7) * 4)));
+          acc[i][j] += v.x; acc[i][j + 1] += v.y; acc[i][j + 2] += v.z; acc[i][j + 3] += v.w;
+        }
+    }
+    __syncthreads();
+  }
+  if (grp == 0) {
+    float ssq = 0.f, tr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gi = ti * TS + ty * 8 + i;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; j4 += 4) {
+        const int gj = tj * TS + tx * 8 + j4;
+        float4 o = make_float4(acc[i][j4], acc[i][j4 + 1], acc[i][j4 + 2], acc[i][j4 + 3]);
+        if (pr.Cadd != nullptr) {
+          const float4 c = *reinterpret_cast<const float4*>(pr.Cadd + (size_t)gi * n + gj);
+          o.x = fmaf(pr.beta, c.x, o.x); o.y = fmaf(pr.beta, c.y, o.y);
+          o.z = fmaf(pr.beta, c.z, o.z); o.w = fmaf(pr.beta, c.w, o.w);
+        }
+        if (gi >= gj && gi < gj + 4) {
+          (&o.x)[gi - gj] += pr.gamma;
+          tr += (&o.x)[gi - gj];
+        }
+        ssq = fmaf(o.x, o.x, ssq); ssq = fmaf(o.y, o.y, ssq); ssq = fmaf(o.z, o.z, ssq); ssq = fmaf(o.w, o.w, ssq);
+        *reinterpret_cast<float4*>(pr.D + (size_t)gi * n + gj) = o;
+      }
+    }
+    if (pr.red_out != nullptr) {  // warp-uniform: grp 0 = warps 0,1
+      ssq = warp_sum(ssq);
+      tr = warp_sum(tr);
+      float* sh = smem_f + 8192;  // beyond the region read above by group 0? (all reads done: safe after barrier)
+      if ((lt & 31) == 0) { sh[(lt >> 5) * 2] = ssq; sh[(lt >> 5) * 2 + 1] = tr; }
+      named_bar_sync(1, 64);
+      if (lt == 0) {
+        const int nt = n / TS;
+        pr.red_out[(ti * nt + tj) * 2] = sh[0] + sh[2];
+        pr.red_out[(ti * nt + tj) * 2 + 1] = sh[1] + sh[3];
+      }
+    }
   }
 }
+constexpr int SGEMM_SMEM = KG * 4 * KC * TS * 4;  // 64 KiB
 
-// ---- block reduction helper (1024 threads)
-__device__ float block_sum_1024(float v, float* s_red) {
+// ---- helpers: grid (5 layers, NB CTAs), 256 threads; reductions via fixed-order partials (deterministic)
+constexpr int NB = 32;
+__device__ __forceinline__ float block_sum_256(float v, float* s_red) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
-  for (int i = 0; i < 32; ++i) t += s_red[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_red[i];
   return t;
+}
+__device__ __forceinline__ void sum_partials(const float* red, int count, float& a, float& b) {
+  a = 0.f; b = 0.f;
+  for (int i = 0; i < count; ++i) { a += red[2 * i]; b += red[2 * i + 1]; }
 }
 
 // covariance from (reduced) raw sums:  mu = sums/N; cov = S_raw/N - mu mu^T + eps I     (ST:171-173, 177)
-__global__ void __launch_bounds__(1024) w2_cov_kernel(const W2Layer* __restrict__ layers, int from_target) {
-  __shared__ float s_red[32];
+// target mode: cov_t from (mean_t, srm_t), plus sum-of-squares partials of cov_t for the NS normalisation.
+__global__ void __launch_bounds__(256) w2_cov_kernel(const W2Layer* __restrict__ layers, int from_target) {
+  __shared__ float s_red[8];
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const float inv_n = from_target ? 1.f : 1.f / L.npix;
   const float* S = from_target ? L.srm_t : L.S_raw;
   const float* sm = from_target ? L.mean_t : L.sums;
-  float* mu = from_target ? L.mean_t : L.mu;
   float* cov = from_target ? L.cov_t : L.cov;
-  if (!from_target)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mu[i] = sm[i] * inv_n;
-  __syncthreads();
-  float tr = 0.f;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+  float ssq = 0.f;
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    float v = S[e] * inv_n - mu[i] * mu[j];
-    if (i == j) { v += L.eps; tr += v; }
+    float v = S[e] * inv_n - (sm[i] * inv_n) * (sm[j] * inv_n);
+    if (i == j) v += L.eps;
     cov[e] = v;
+    ssq = fmaf(v, v, ssq);
   }
-  tr = block_sum_1024(tr, s_red);
-  float md = 0.f;
-  if (!from_target)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = mu[i] - L.mean_t[i]; md += d * d; }
-  md = block_sum_1024(md, s_red);
-  if (threadIdx.x == 0) {
-    if (from_target) L.scal[W2S_TR_COV_T] = tr;
-    else { L.scal[W2S_TR_COV] = tr; L.scal[W2S_MEAN_DIFF] = md / n; }
+  ssq = block_sum_256(ssq, s_red);
+  if (threadIdx.x == 0) { L.red[blockIdx.y * 2] = ssq; L.red[blockIdx.y * 2 + 1] = 0.f; }
+  if (blockIdx.y == 0) {
+    float tr = 0.f, md = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float m = sm[i] * inv_n;
+      tr += S[(size_t)i * n + i] * inv_n - m * m + L.eps;
+      if (!from_target) {
+        L.mu[i] = m;
+        const float d = m - L.mean_t[i];
+        md += d * d;
+      }
+    }
+    tr = block_sum_256(tr, s_red);
+    md = block_sum_256(md, s_red);
+    if (threadIdx.x == 0) {
+      if (from_target) L.scal[W2S_TR_COV_T] = tr;
+      else { L.scal[W2S_TR_COV] = tr; L.scal[W2S_MEAN_DIFF] = md / n; }
+    }
   }
 }
 
-// Y = M / ||M||_F, Z = I        (SQ:15-19)
-__global__ void __launch_bounds__(1024) w2_ns_init_kernel(const W2Layer* __restrict__ layers, int from_target) {
-  __shared__ float s_red[32];
+// Y = M / ||M||_F, Z = I        (SQ:15-19).  ||M||^2 arrives as partials (cov kernel: NB; GEMM tiles: (n/64)^2)
+__global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restrict__ layers, int from_target) {
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const float* M = from_target ? L.cov_t : L.M;
-  float ss = 0.f;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) ss = fmaf(M[e], M[e], ss);
-  ss = block_sum_1024(ss, s_red);
+  float ss, dummy;
+  sum_partials(L.red, from_target ? NB : (n / TS) * (n / TS), ss, dummy);
   const float norm = sqrtf(ss);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
     L.Y[0][e] = M[e] / norm;
     L.Z[0][e] = (i == j) ? 1.f : 0.f;
   }
-  if (threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
+  if (blockIdx.y == 0 && threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
 }
 
 // target: P = Y sqrt(norm)                                              (ST:159, SQ:25)
-__global__ void __launch_bounds__(1024) w2_target_finish_kernel(const W2Layer* __restrict__ layers) {
+__global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __restrict__ layers) {
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const float s = sqrtf(L.scal[W2S_NORM_A]);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) L.P[e] = L.Y[0][e] * s;
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) L.P[e] = L.Y[0][e] * s;
 }
 
-// forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41)
-__global__ void __launch_bounds__(1024) w2_fwd_finish_kernel(const W2Layer* __restrict__ layers, float* loss_terms) {
-  __shared__ float s_red[32];
+// forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41).
+// ||Y||^2 and tr(Y) arrive as per-tile partials written by the last NS round.
+__global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __restrict__ layers, float* loss_terms) {
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const float* Y = L.Y[0];
-  float ss = 0.f, tr = 0.f;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const float v = Y[e];
-    ss = fmaf(v, v, ss);
-    if (e / n == e % n) tr += v;
-  }
-  ss = block_sum_1024(ss, s_red);
-  tr = block_sum_1024(tr, s_red);
+  float ss, tr;
+  sum_partials(L.red, (n / TS) * (n / TS), ss, tr);
   const float sq = sqrtf(L.scal[W2S_NORM_A]);
   const float norm_y = sqrtf(ss);
-  const float norm_r = sq * norm_y;         // ||R||_F
+  const float norm_r = sq * norm_y;                     // ||R||_F
   const float tr_r = tr * sq;
-  const float seed = -2.f * L.weight / (n * norm_r);  // grad_output / norm_z with grad_output = -2 w / C * I
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    L.A[0][e] = Y[e] / norm_y;                        // a = z / ||z||
-    L.Q[0][e] = (e / n == e % n) ? seed : 0.f;
+  const float seed = -2.f * L.weight / (n * norm_r);    // grad_output / ||z|| with grad_output = -2 w / C * I
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
+    const int i = e / n, j = e - i * n;
+    L.A[0][e] = Y[e] / norm_y;                          // a = z / ||z||
+    L.Q[0][e] = (i == j) ? seed : 0.f;
   }
-  if (threadIdx.x == 0) {
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
     const float cov_diff = (L.scal[W2S_TR_COV_T] + L.scal[W2S_TR_COV] - 2.f * tr_r) / n;
     const float l = (L.scal[W2S_MEAN_DIFF] + cov_diff) * L.weight;
     L.scal[W2S_LOSS] = l;
@@ -206,23 +288,29 @@ __global__ void __launch_bounds__(1024) w2_fwd_finish_kernel(const W2Layer* __re
   }
 }
 
-// backward finish: Gs = Gc + Gc^T; gmu = 2w(mu - mu_t)/C - Gs mu; emit bf16 Gs/N ([C][C]) and fp32 gmu/N
-__global__ void __launch_bounds__(1024) w2_bwd_finish_kernel(const W2Layer* __restrict__ layers) {
+// backward finish 1: Gs = Gc + Gc^T; bf16 Gs/N ([C][C]) for the tap-gradient GEMM
+__global__ void __launch_bounds__(256) w2_bwd_finish_kernel(const W2Layer* __restrict__ layers) {
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const float inv_n = 1.f / L.npix;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    const float gs = L.Gc[e] + L.Gc[j * n + i];
+    const float gs = L.Gc[e] + L.Gc[(size_t)j * n + i];
     L.Gs[e] = gs;
     L.gs_bf16[e] = __float2bfloat16(gs * inv_n);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+}
+// backward finish 2: gmu = 2w(mu - mu_t)/C - Gs mu  (one warp per row), emitted divided by N
+__global__ void __launch_bounds__(256) w2_gmu_kernel(const W2Layer* __restrict__ layers) {
+  const W2Layer L = layers[blockIdx.x];
+  const int n = L.n;
+  const int lane = threadIdx.x & 31;
+  const float inv_n = 1.f / L.npix;
+  for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < n; i += NB * 8) {
     float s = 0.f;
-    for (int j = 0; j < n; ++j) s = fmaf(L.Gs[i * n + j], L.mu[j], s);
-    const float gm = 2.f * L.weight * (L.mu[i] - L.mean_t[i]) / n - s;
-    L.gmu_bias[i] = gm * inv_n;
+    for (int j = lane; j < n; j += 32) s = fmaf(L.Gs[(size_t)i * n + j], L.mu[j], s);
+    s = warp_sum(s);
+    if (lane == 0) L.gmu_bias[i] = (2.f * L.weight * (L.mu[i] - L.mean_t[i]) / n - s) * inv_n;
   }
 }
 
@@ -231,7 +319,7 @@ __global__ void __launch_bounds__(1024) w2_bwd_finish_kernel(const W2Layer* __re
 // ================================================================================================ host engine
 size_t W2Engine::layer_floats(int n) {
   // cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, X1, X23, U, Gc, Gs, P, cov_t, srm_t  (21 matrices) + vectors
-  return (size_t)21 * n * n + 8 * (size_t)n + 64;
+  return (size_t)21 * n * n + 8 * (size_t)n + 64 + 2 * NRED + 256;
 }
 
 size_t W2Engine::workspace_bytes() {
@@ -252,8 +340,9 @@ static void add_prob(std::vector<GemmProb>& probs, std::vector<uint32_t>& tiles,
 
 static GemmProb mk(int n, float* D, const float* A, int tA, const float* B, int tB, float alpha, float gamma = 0.f,
                    const float* Cadd = nullptr, float beta = 0.f, const float* A2 = nullptr, int tA2 = 0,
-                   const float* B2 = nullptr, int tB2 = 0, float alpha2 = 0.f) {
+                   const float* B2 = nullptr, int tB2 = 0, float alpha2 = 0.f, float* red_out = nullptr) {
   GemmProb p{};
+  p.red_out = red_out;
   p.A = A; p.B = B; p.A2 = A2; p.B2 = B2; p.Cadd = Cadd; p.D = D; p.n = n;
   p.transA = tA; p.transB = tB; p.transA2 = tA2; p.transB2 = tB2;
   p.alpha = alpha; p.alpha2 = alpha2; p.beta = beta; p.gamma = gamma;
@@ -280,6 +369,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     L.S_raw = nullptr; L.sums = nullptr;  // bound per plan (stats buffer)
     L.mu = (float*)take(n * 4); L.mean_t = (float*)take(n * 4); L.gmu_bias = (float*)take(n * 4);
     L.scal = (float*)take(64 * 4);
+    L.red = (float*)take(2 * NRED * 4);
     L.gs_bf16 = (bf16*)take((size_t)n * n * 2);
     L.weight = 0.f; L.npix = 1.f;
   }
@@ -303,8 +393,9 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
       begin_round();
       for (int l = 0; l < 5; ++l) {
         W2Layer& L = host_layers[l];
-        add_prob(probs, tiles, mk(L.n, L.Y[d], L.Y[s], 0, L.T, 0, 1.f));
-        add_prob(probs, tiles, mk(L.n, L.Z[d], L.T, 0, L.Z[s], 0, 1.f));
+        add_prob(probs, tiles, mk(L.n, L.Y[d], L.Y[s], 0, L.T, 0, 1.f, 0.f, nullptr, 0.f, nullptr, 0, nullptr, 0, 0.f,
+                                  it == 11 ? L.red : nullptr));
+        if (it < 11) add_prob(probs, tiles, mk(L.n, L.Z[d], L.T, 0, L.Z[s], 0, 1.f));  // Z is dead after the last Y
       }
       end_round();
     }
@@ -319,12 +410,18 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.X, L.P, 0, L.cov, 0, 1.f)); }
   end_round();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.M, L.X, 0, L.P, 0, 1.f)); }
+  for (int l = 0; l < 5; ++l) {
+    W2Layer& L = host_layers[l];
+    add_prob(probs, tiles, mk(L.n, L.M, L.X, 0, L.P, 0, 1.f, 0.f, nullptr, 0.f, nullptr, 0, nullptr, 0, 0.f, L.red));
+  }
   end_round();
   r_fwd_ns_begin = (int)rounds.size();
   ns_rounds();
   r_fwd_end = (int)rounds.size();
-  // (c) backward: 12 x { E = 3I - a a ; X1 = q E, X23 = a^T q - q a, a' = a E / 2 ; q' = X1/2 - a^T X23 / 2 }
+  // (c) backward, SQ:42-46:  E = 3I - a a;  q' = (q E - a^T (a^T q - q a)) / 2;  a' = a E / 2.
+  // On this path grad_output is always a multiple of I (d/dR of -2 w tr(R)/C), `a` is symmetric and every q is a
+  // polynomial in `a`, so the commutator a^T q - q a is identically zero in exact arithmetic (the reference
+  // evaluates its rounding noise, ~1e-7 relative); the schedule below drops it:  q' = q E / 2.
   r_bwd_begin = (int)rounds.size();
   for (int it = 0; it < 12; ++it) {
     const int s = it & 1, d = s ^ 1;
@@ -334,15 +431,8 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     begin_round();
     for (int l = 0; l < 5; ++l) {
       W2Layer& L = host_layers[l];
-      add_prob(probs, tiles, mk(L.n, L.X1, L.Q[s], 0, L.E, 0, 1.f));
-      add_prob(probs, tiles, mk(L.n, L.X23, L.A[s], 1, L.Q[s], 0, 1.f, 0.f, nullptr, 0.f, L.Q[s], 0, L.A[s], 0, -1.f));
+      add_prob(probs, tiles, mk(L.n, L.Q[d], L.Q[s], 0, L.E, 0, 0.5f));
       if (it < 11) add_prob(probs, tiles, mk(L.n, L.A[d], L.A[s], 0, L.E, 0, 0.5f));
-    }
-    end_round();
-    begin_round();
-    for (int l = 0; l < 5; ++l) {
-      W2Layer& L = host_layers[l];
-      add_prob(probs, tiles, mk(L.n, L.Q[d], L.A[s], 1, L.X23, 0, -0.5f, 0.f, L.X1, 0.5f));
     }
     end_round();
   }
@@ -376,8 +466,13 @@ int W2Engine::upload_layers(cudaStream_t s) {
 }
 
 int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    STB_CUDA_CHECK(cudaFuncSetAttribute(sgemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SGEMM_SMEM));
+    attr_set = true;
+  }
   for (int r = r0; r < r1; ++r) {
-    sgemm_grouped_kernel<<<rounds[r].n_tiles, 256, 0, s>>>(d_probs, d_tiles + rounds[r].first_tile);
+    sgemm_grouped_kernel<<<rounds[r].n_tiles, KG * 64, SGEMM_SMEM, s>>>(d_probs, d_tiles + rounds[r].first_tile);
   }
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
@@ -385,22 +480,25 @@ int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
 
 int W2Engine::build_targets(cudaStream_t s) {
   // srm_t / mean_t already hold the blended target moments (ST:443-450)
-  w2_cov_kernel<<<5, 1024, 0, s>>>(d_layers, 1);
-  w2_ns_init_kernel<<<5, 1024, 0, s>>>(d_layers, 1);
+  const dim3 grid(5, NB);
+  w2_cov_kernel<<<grid, 256, 0, s>>>(d_layers, 1);
+  w2_ns_init_kernel<<<grid, 256, 0, s>>>(d_layers, 1);
   STB_TRY(run_rounds(r_target_begin, r_target_end, s));
-  w2_target_finish_kernel<<<5, 1024, 0, s>>>(d_layers);
+  w2_target_finish_kernel<<<grid, 256, 0, s>>>(d_layers);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
 
 int W2Engine::forward_backward(float* loss_terms, cudaStream_t s) {
-  w2_cov_kernel<<<5, 1024, 0, s>>>(d_layers, 0);
+  const dim3 grid(5, NB);
+  w2_cov_kernel<<<grid, 256, 0, s>>>(d_layers, 0);
   STB_TRY(run_rounds(r_fwd_begin, r_fwd_ns_begin, s));
-  w2_ns_init_kernel<<<5, 1024, 0, s>>>(d_layers, 0);
+  w2_ns_init_kernel<<<grid, 256, 0, s>>>(d_layers, 0);
   STB_TRY(run_rounds(r_fwd_ns_begin, r_fwd_end, s));
-  w2_fwd_finish_kernel<<<5, 1024, 0, s>>>(d_layers, loss_terms);
+  w2_fwd_finish_kernel<<<grid, 256, 0, s>>>(d_layers, loss_terms);
   STB_TRY(run_rounds(r_bwd_begin, r_bwd_end, s));
-  w2_bwd_finish_kernel<<<5, 1024, 0, s>>>(d_layers);
+  w2_bwd_finish_kernel<<<grid, 256, 0, s>>>(d_layers);
+  w2_gmu_kernel<<<grid, 256, 0, s>>>(d_layers);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
