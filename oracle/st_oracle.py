@@ -145,8 +145,8 @@ def vgg_forward(image, weights, pooling='max', last_layer=29, sim_bf16=False):
         if kind == 'conv':
             wt, b = weights[ci]
             wt, b = wt.to(x.dtype), b.to(x.dtype)
-            if sim_bf16 and ci > 0:
-                wt = _q(wt, True)
+            if sim_bf16:
+                wt = _q(wt, True)  # every conv (conv0 included) takes bf16 weights on the tensor cores
             if i == 0:
                 x = F.conv2d(F.pad(x, (1, 1, 1, 1), mode='replicate'), wt, b)  # ST:39, 52-59
             else:
@@ -178,7 +178,7 @@ def vgg_backward(tap_grads, acts, weights, pooling='max', sim_bf16=False):
         else:
             wt = weights[ci][0].to(g.dtype)
             if i == 0:
-                gp = F.conv_transpose2d(g, wt)  # gradient on the replicate-padded grid (H+2, W+2)
+                gp = F.conv_transpose2d(g, _q(wt, sim_bf16))  # gradient on the replicate-padded grid (H+2, W+2)
                 # fold the pad ring back onto the border pixels (adjoint of replicate padding)
                 gp[:, :, 1, :] += gp[:, :, 0, :]
                 gp[:, :, -2, :] += gp[:, :, -1, :]

@@ -111,7 +111,7 @@ void make_plan(const stb_ctx* ctx, int H, int W, Plan* pl) {
   pl->g_off[0] = take(gmax);
   pl->g_off[1] = take(gmax);
   pl->gtv_off = take((size_t)3 * H * W * 4);
-  pl->n_tv_partials = ((W + 127) / 128) * H;
+  pl->n_tv_partials = ((W + 255) / 256) * H;
   pl->tvp_off = take((size_t)pl->n_tv_partials * 4);
   pl->ssep_off = take(1024 * 4);
   size_t gp = 0;
@@ -151,8 +151,16 @@ T* at(const stb_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->ws + of
 int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool do_tv, cudaStream_t s) {
   int ntv = 0;
   ctx->prof.begin(PC_CONV0_FWD, s);
-  STB_TRY(launch_conv0_fwd(img, ctx->w0, ctx->bias[0], at<bf16>(ctx, pl.act_off[0]), pl.H, pl.W, ctx->tv_weight,
-                           do_tv ? at<float>(ctx, pl.gtv_off) : nullptr, at<float>(ctx, pl.tvp_off), &ntv, s));
+  if (do_tv)
+    STB_TRY(launch_tv(img, pl.H, pl.W, ctx->tv_weight, at<float>(ctx, pl.gtv_off), at<float>(ctx, pl.tvp_off), &ntv, s));
+  {  // conv0 on the tensor cores: im2col (hi/lo bf16 split, replicate pad, Normalize) + 1x1 pixel-GEMM + bias + ReLU
+    bf16* col = at<bf16>(ctx, pl.g_off[0]);  // the gradient ping-pong buffer is idle during the forward pass
+    STB_TRY(launch_im2col0(img, col, pl.H, pl.W, s));
+    PixelGemmArgs a;
+    a.H = pl.H; a.W = pl.W; a.Cin = 0; a.Cout = 64; a.C2 = 64; a.mode = 0;
+    a.A2 = col; a.B2 = ctx->wf[0]; a.out = at<bf16>(ctx, pl.act_off[0]); a.bias = ctx->bias[0];
+    STB_TRY(launch_pixel_gemm(a, s));
+  }
   ctx->prof.end(s);
   int np = 0;
   const bf16* cur = at<bf16>(ctx, pl.act_off[0]);
@@ -242,7 +250,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
   size_t bytes = 0;
   for (int i = 0; i < NCONV; ++i) {
     bytes += align_up((size_t)kCout[i] * 4, 256);
-    if (i == 0) bytes += align_up((size_t)64 * 27 * 4, 256);
+    if (i == 0) bytes += align_up((size_t)64 * 27 * 4, 256) + align_up((size_t)9 * 64 * 64 * 2, 256) + 8192;
     else bytes += 2 * align_up((size_t)9 * kCout[i] * kCin[i] * 2, 256);
   }
   cudaError_t e = cudaMalloc(&ctx->owned, bytes);
@@ -255,6 +263,10 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
     if (i == 0) {
       ctx->w0 = (float*)take(64 * 27 * 4);
       STB_CUDA_CHECK(cudaMemcpyAsync(ctx->w0, conv_w[0], 64 * 27 * 4, cudaMemcpyDeviceToDevice, s));
+      ctx->wb[0] = (bf16*)take((size_t)9 * 64 * 64 * 2);
+      STB_TRY(pack_weights_conv0_bwd(ctx->w0, ctx->wb[0], s));
+      ctx->wf[0] = (bf16*)take((size_t)64 * 64 * 2);
+      STB_TRY(pack_weights_conv0_fwd(ctx->w0, ctx->wf[0], s));
     } else {
       ctx->wf[i] = (bf16*)take((size_t)9 * kCout[i] * kCin[i] * 2);
       ctx->wb[i] = (bf16*)take((size_t)9 * kCout[i] * kCin[i] * 2);
@@ -461,9 +473,18 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
     as.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     as.eps = adam_eps; as.ema_decay = ema_decay; as.one_minus_decay = 1.f - ema_decay;
   }
+  // conv0 dgrad of the interior on the tensor cores (output channels zero-padded 3 -> 64), borders + update in SIMT
+  {
+    PixelGemmArgs a;
+    a.H = H; a.W = W; a.Cin = 64; a.Cout = 64; a.mode = 2;
+    a.A = g[cur]; a.Bw = ctx->wb[0]; a.out = g[cur ^ 1];
+    ctx->prof.begin(PC_CONV_BWD, s);
+    STB_TRY(launch_pixel_gemm(a, s));
+    ctx->prof.end(s);
+  }
   ctx->prof.begin(PC_CONV0_BWD_ADAM, s);
-  STB_TRY(launch_conv0_bwd_adam(g[cur], ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema, grad_out,
-                                H, W, as, apply_update, s));
+  STB_TRY(launch_conv0_bwd_adam(g[cur], g[cur ^ 1], ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
+                                grad_out, H, W, as, apply_update, s));
   ctx->prof.end(s);
   ctx->prof.begin(PC_FINALIZE, s);
   finalize_loss_kernel<<<1, 1024, 0, s>>>(at<float>(ctx, pl.ssep_off), n_sse, ctx->content_weight / (float)n22,

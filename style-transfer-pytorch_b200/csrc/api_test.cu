@@ -41,15 +41,48 @@ extern "C" {
 
 int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void* out_bf16, int H, int W,
                        float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream) {
-  return launch_conv0_fwd(img, w0, b0, static_cast<bf16*>(out_bf16), H, W, tv_weight, gtv, tv_partials, n_partials,
-                          static_cast<cudaStream_t>(stream));
+  // product path of conv0: TV kernel, im2col (hi/lo split) and the 1x1 tcgen05 pixel-GEMM with bias + ReLU
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (gtv != nullptr) STB_TRY(launch_tv(img, H, W, tv_weight, gtv, tv_partials, n_partials, s));
+  bf16 *col = nullptr, *wp = nullptr;
+  STB_CUDA_CHECK(cudaMalloc(&col, (size_t)H * W * 64 * 2));
+  STB_CUDA_CHECK(cudaMalloc(&wp, 64 * 64 * 2));
+  int rc = pack_weights_conv0_fwd(w0, wp, s);
+  if (rc == 0) rc = launch_im2col0(img, col, H, W, s);
+  if (rc == 0) {
+    PixelGemmArgs a;
+    a.H = H; a.W = W; a.Cin = 0; a.Cout = 64; a.C2 = 64; a.mode = 0;
+    a.A2 = col; a.B2 = wp; a.out = static_cast<bf16*>(out_bf16); a.bias = b0;
+    rc = launch_pixel_gemm(a, s);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(col);
+  cudaFree(wp);
+  return rc;
 }
 
 int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
                        void* stream) {
+  // product path: interior via the tcgen05 dgrad (weights zero-padded 3 -> 64 channels), borders in SIMT
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   AdamScalars as{};
-  return launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), w0, gtv, nullptr, nullptr, nullptr, nullptr,
-                               grad_out, H, W, as, 0, static_cast<cudaStream_t>(stream));
+  bf16 *gint = nullptr, *wp = nullptr;
+  STB_CUDA_CHECK(cudaMalloc(&gint, (size_t)H * W * 64 * 2));
+  STB_CUDA_CHECK(cudaMalloc(&wp, 9 * 64 * 64 * 2));
+  int rc = pack_weights_conv0_bwd(w0, wp, s);
+  if (rc == 0) {
+    PixelGemmArgs a;
+    a.H = H; a.W = W; a.Cin = 64; a.Cout = 64; a.mode = 2;
+    a.A = static_cast<const bf16*>(g0_bf16); a.Bw = wp; a.out = gint;
+    rc = launch_pixel_gemm(a, s);
+  }
+  if (rc == 0)
+    rc = launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), gint, w0, gtv, nullptr, nullptr, nullptr, nullptr,
+                               grad_out, H, W, as, 0, s);
+  cudaStreamSynchronize(s);
+  cudaFree(gint);
+  cudaFree(wp);
+  return rc;
 }
 
 int stb_test_pool(int pooling, int backward, const void* in_or_gout, const void* y, void* out, int H, int W, int C,

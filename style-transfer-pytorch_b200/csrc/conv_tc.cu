@@ -7,8 +7,9 @@
 //               wgrad), the ReLU `threshold_backward`, and the Gram/mean backward `dL/dF = F(G+G^T)/N + 1 gmu^T/N`
 //               of ST:163-168 which is folded in as extra K-blocks accumulating into the same TMEM tile.
 //
-// Tiling: one CTA tile = 16x8 output pixels (M = 128 TMEM lanes) x BN output channels (BN in {64,128,256} fp32
-// TMEM columns), K = 9 taps x Cin.  Persistent CTAs (one per SM) walk tiles; three roles:
+// Tiling: one CTA tile = MT horizontally adjacent sub-tiles of 16x8 output pixels (M = 128 TMEM lanes each) x BN
+// output channels (BN in {64,128,256} fp32 TMEM columns; MT = 2 for BN <= 128 so that every weight stage feeds two
+// sub-tiles), K = 9 taps x Cin.  Persistent CTAs (one per SM) walk tiles; three roles:
 //   warp 0      TMA producer: per 64-channel chunk it loads three "dx buffers" (18 rows x 8 px x 64 ch, SW128,
 //               zero-filled out of bounds = the conv's zero padding); the three dy taps are 1 KiB-aligned row
 //               shifts inside a dx buffer, so each activation byte is fetched 3.4x instead of 9x from L2.
@@ -22,22 +23,27 @@ namespace stb {
 
 namespace {
 
-constexpr int TILE_H = 16, TILE_W = 8;           // output pixels per tile = 128 = UMMA M
+constexpr int TILE_H = 16, TILE_W = 8;           // output pixels per sub-tile = 128 = UMMA M
 constexpr int A_ROWS = TILE_H + 2;               // dx buffer rows (halo above/below)
-constexpr int A_STAGE_BYTES = A_ROWS * 1024;     // 18 KiB: rows of 8 pixels x 64 ch x 2 B
-constexpr int A2_BYTES = TILE_H * 1024;          // centre box for the 1x1 source
 constexpr int STG_BYTES = TILE_H * 1024;         // 128 pixels x 64 ch bf16 staging for the TMA store
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 
+// MT = horizontally adjacent 16x8 sub-tiles per CTA tile that share every weight stage (halves the L2->smem
+// weight traffic per MMA for the narrow-N layers, which are L2-bandwidth bound otherwise).
 template <int BN>
 struct Cfg {
-  static constexpr int NA = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
-  static constexpr int NB = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int MT = BN == 256 ? 1 : 2;
+  static constexpr int NA = 3;
+  static constexpr int NB = BN == 64 ? 8 : 4;
+  static constexpr int A_PITCH = MT * 1024;                 // bytes per row of 8*MT pixels
+  static constexpr int A_STAGE_BYTES = A_ROWS * A_PITCH;    // dx buffer: 18 rows x 8*MT px x 64 ch
+  static constexpr int A2_BYTES = TILE_H * A_PITCH;         // centre box for the 1x1 source
   static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NA * A_STAGE_BYTES;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
   static constexpr int OFF_STG = OFF_B + NB * B_STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_STG + 2 * STG_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 512 * 4;
@@ -109,12 +115,12 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tn = tile % p.n_tiles_n;
         const int t2 = tile / p.n_tiles_n;
         const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-        const int y0 = ty * TILE_H, x0 = tx * TILE_W, n0 = tn * BN;
+        const int y0 = ty * TILE_H, x0 = tx * TILE_W * C::MT, n0 = tn * BN;
         for (int c = 0; c < n_chunks; ++c) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(&a_empty[sa], pa ^ 1);
-            mbar_expect_tx(&a_full[sa], A_STAGE_BYTES);
-            tma_load_3d(smem + C::OFF_A + sa * A_STAGE_BYTES, &tmA, &a_full[sa], c * 64, x0 + dx - 1, y0 - 1);
+            mbar_expect_tx(&a_full[sa], C::A_STAGE_BYTES);
+            tma_load_3d(smem + C::OFF_A + sa * C::A_STAGE_BYTES, &tmA, &a_full[sa], c * 64, x0 + dx - 1, y0 - 1);
             if (++sa == C::NA) { sa = 0; pa ^= 1; }
             for (int dy = 0; dy < 3; ++dy) {
               mbar_wait(&b_empty[sb], pb ^ 1);
@@ -126,8 +132,8 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int c = 0; c < n_chunks2; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], A2_BYTES);
-          tma_load_3d(smem + C::OFF_A + sa * A_STAGE_BYTES, &tmA2, &a_full[sa], c * 64, x0, y0 - p.a2_row0);
+          mbar_expect_tx(&a_full[sa], C::A2_BYTES);
+          tma_load_3d(smem + C::OFF_A + sa * C::A_STAGE_BYTES, &tmA2, &a_full[sa], c * 64, x0, y0 - p.a2_row0);
           if (++sa == C::NA) { sa = 0; pa ^= 1; }
           mbar_wait(&b_empty[sb], pb ^ 1);
           mbar_expect_tx(&b_full[sb], C::B_STAGE_BYTES);
@@ -148,24 +154,26 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        uint32_t accum = 0;
+        const uint32_t tmem_d = tmem_base + acc * (C::MT * BN);
+        uint32_t accum = 0;  // 0 only for the first weight stage of the tile (per-sub-tile accumulators)
         for (int c = 0; c < n_chunks; ++c) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
-            const uint32_t a_stage = a_base0 + sa * A_STAGE_BYTES;
+            const uint32_t a_stage = a_base0 + sa * C::A_STAGE_BYTES;
             for (int dy = 0; dy < 3; ++dy) {
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              const uint32_t a_addr = a_stage + dy * 1024;
               const uint32_t b_addr = b_base0 + sb * C::B_STAGE_BYTES;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                          umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum);
-                accum = 1;
+              for (int m = 0; m < C::MT; ++m) {
+                const uint32_t a_addr = a_stage + dy * C::A_PITCH + m * 1024;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d + m * BN, umma_desc_sw128(a_addr + k * 32, 16, C::A_PITCH),
+                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum | (k > 0));
               }
+              accum = 1;
               umma_commit(&b_empty[sb]);
               if (++sb == C::NB) { sb = 0; pb ^= 1; }
             }
@@ -177,14 +185,16 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&a_full[sa], pa);
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const uint32_t a_addr = a_base0 + sa * A_STAGE_BYTES;
           const uint32_t b_addr = b_base0 + sb * C::B_STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                      umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum);
-            accum = 1;
+          for (int m = 0; m < C::MT; ++m) {
+            const uint32_t a_addr = a_base0 + sa * C::A_STAGE_BYTES + m * 1024;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + m * BN, umma_desc_sw128(a_addr + k * 32, 16, C::A_PITCH),
+                        umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum | (k > 0));
           }
+          accum = 1;
           umma_commit(&b_empty[sb]);
           if (++sb == C::NB) { sb = 0; pb ^= 1; }
           umma_commit(&a_empty[sa]);
@@ -207,18 +217,18 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tn = tile % p.n_tiles_n;
       const int t2 = tile / p.n_tiles_n;
       const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-      const int y0 = ty * TILE_H, x0 = tx * TILE_W, n0 = tn * BN;
-      const int py = y0 + (r >> 3), px = x0 + (r & 7);
-      const bool inb = (py < p.H) && (px < p.W);
-      const bool in_rows = (py >= p.row_lo) && (py < p.row_hi);
-      const size_t pix_off = (static_cast<size_t>(py) * p.W + px) * p.Cout + n0;
-
+      const int y0 = ty * TILE_H, n0 = tn * BN;
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
-
 #pragma unroll 1
-      for (int j = 0; j < BN / 64; ++j) {
+      for (int mj = 0; mj < C::MT * (BN / 64); ++mj) {
+        const int m = mj / (BN / 64), j = mj % (BN / 64);
+        const int x0 = (tx * C::MT + m) * TILE_W;
+        const int py = y0 + (r >> 3), px = x0 + (r & 7);
+        const bool inb = (py < p.H) && (px < p.W);
+        const bool in_rows = (py >= p.row_lo) && (py < p.row_hi);
+        const size_t pix_off = (static_cast<size_t>(py) * p.W + px) * p.Cout + n0;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + (acc * C::MT + m) * BN;
         uint8_t* stage = smem + C::OFF_STG + stg * STG_BYTES;
         // make sure the TMA store that last read this staging buffer is done, then let everyone write
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -334,7 +344,9 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   const int BN = a.Cout >= 256 ? 256 : a.Cout;
   KParams kp;
   kp.H = a.H; kp.W = a.W; kp.Cin = a.Cin; kp.Cout = a.Cout; kp.C2 = a.C2;
-  kp.tiles_x = (a.W + TILE_W - 1) / TILE_W;
+  const int MT = BN == 256 ? 1 : 2;  // must match Cfg<BN>::MT
+  const int tile_w = TILE_W * MT;
+  kp.tiles_x = (a.W + tile_w - 1) / tile_w;
   kp.tiles_y = (a.H + TILE_H - 1) / TILE_H;
   kp.n_tiles_n = a.Cout / BN;
   kp.total_tiles = kp.tiles_x * kp.tiles_y * kp.n_tiles_n;
@@ -350,12 +362,12 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   STB_TRY(make_tmap_bf16_3d(&tmOut, a.out, a.Cout, W, H, a.Cout * 2ull, W * a.Cout * 2ull, 64, TILE_W, TILE_H));
   tmA = tmB = tmA2 = tmB2 = tmOut;
   if (a.Cin > 0) {
-    STB_TRY(make_tmap_bf16_3d(&tmA, a.A, a.Cin, W, H, a.Cin * 2ull, W * a.Cin * 2ull, 64, TILE_W, A_ROWS));
+    STB_TRY(make_tmap_bf16_3d(&tmA, a.A, a.Cin, W, H, a.Cin * 2ull, W * a.Cin * 2ull, 64, tile_w, A_ROWS));
     STB_TRY(make_tmap_bf16_3d(&tmB, a.Bw, a.Cin, a.Cout, 9, a.Cin * 2ull, (uint64_t)a.Cout * a.Cin * 2ull, 64, BN, 1));
   }
   if (a.C2 > 0) {
     const int rows = a.a2_rows > 0 ? a.a2_rows : a.H;
-    STB_TRY(make_tmap_bf16_3d(&tmA2, a.A2, a.C2, W, rows, a.C2 * 2ull, W * a.C2 * 2ull, 64, TILE_W, TILE_H));
+    STB_TRY(make_tmap_bf16_3d(&tmA2, a.A2, a.C2, W, rows, a.C2 * 2ull, W * a.C2 * 2ull, 64, tile_w, TILE_H));
     STB_TRY(make_tmap_bf16_3d(&tmB2, a.B2, a.C2, a.Cout, 1, a.C2 * 2ull, (uint64_t)a.Cout * a.C2 * 2ull, 64, BN, 1));
   }
   if (a.mode == 0) {
@@ -389,6 +401,22 @@ __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ ou
   }
 }
 }  // namespace
+
+namespace {
+__global__ void pack_w0_bwd_kernel(const float* __restrict__ w0, bf16* __restrict__ out) {
+  // out[tap][ci][co] = w0[co][ci][8 - tap] for ci < 3, else 0
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * 64 * 64; i += gridDim.x * blockDim.x) {
+    const int co = i & 63, ci = (i >> 6) & 63, tap = i >> 12;
+    out[i] = __float2bfloat16(ci < 3 ? w0[(co * 3 + ci) * 9 + (8 - tap)] : 0.f);
+  }
+}
+}  // namespace
+
+int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s) {
+  pack_w0_bwd_kernel<<<64, 256, 0, s>>>(w0, out);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
 
 int pack_weights_fwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
   pack_w_kernel<<<256, 256, 0, s>>>(w, out, Cout, Cin, 0);

@@ -1,8 +1,10 @@
 // HBM-bound kernels on either side of the tensor-core trunk:
-//   conv0_fwd_tv   : Normalize (ST:30-31,85) + replicate-pad conv 3->64 + bias + ReLU (ST:39,52-59) -> bf16 NHWC,
-//                    fused with the nine-point TV loss and its gradient on the raw image (ST:184-195)
-//   conv0_bwd_adam : conv0 dgrad (adjoint of replicate pad) + Normalize backward + TV gradient -> Adam step
-//                    (torch/optim/adam.py:413-546 single-tensor math) -> clamp_(0,1) (ST:483-485) -> EMA (ST:250-253)
+//   im2col0        : Normalize (ST:30-31,85) + replicate-pad (ST:39,52-59) im2col of the image, hi/lo bf16 split, so
+//                    that conv0 itself runs as a 1x1 pixel-GEMM on the tensor cores (conv_tc.cu)
+//   tv             : nine-point TV loss and its gradient on the raw image (ST:184-195)
+//   conv0_bwd_adam : border part of the conv0 dgrad (adjoint of replicate pad; the interior comes from the tensor
+//                    cores) + Normalize backward + TV gradient -> Adam step (torch/optim/adam.py:413-546
+//                    single-tensor math) -> clamp_(0,1) (ST:483-485) -> EMA (ST:250-253)
 //   pool2x2 fwd/bwd: MaxPool2d(2) / Scale(AvgPool2d(2),2.0) / Scale(LPPool2d(2,2),0.78)  (ST:21-22,41-46)
 //   content_sse    : sum((F22 - T)^2)  (ST:119-126)
 #include "kernels.h"
@@ -49,144 +51,119 @@ __device__ float tv_gpad_slow(const float* __restrict__ x, int H, int W, int a, 
   return g;
 }
 
-// block = 128 threads = 4 warps; warp w owns output channels [16w, 16w+16) (weights are warp-uniform smem broadcasts),
-// lane l owns the 4 consecutive pixels x0..x0+3 with x0 = (blockIdx.x*32 + l)*4.  grid: (ceil(W/128), H).
-__global__ void __launch_bounds__(128)
-conv0_fwd_tv_kernel(const float* __restrict__ img, const float* __restrict__ w0, const float* __restrict__ b0,
-                    bf16* __restrict__ out, int H, int W, int do_tv, TvConst tc, float* __restrict__ gtv,
-                    float* __restrict__ tv_partials) {
-  __shared__ __align__(16) float s_w[27 * 64];  // [k = (c*3+ky)*3+kx][co]
-  __shared__ float s_b[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += 128) {
-    const int co = i & 63, k = i >> 6;
-    s_w[i] = w0[co * 27 + k];
-  }
-  if (threadIdx.x < 64) s_b[threadIdx.x] = b0[threadIdx.x];
-  __syncthreads();
-
+// Nine-point L2 TV loss (ST:184-195) and its gradient (times tv_weight) on the raw image.  One thread per pixel,
+// all three channels; block partials of the loss are summed in fixed order by finalize_loss.
+__global__ void __launch_bounds__(256)
+tv_kernel(const float* __restrict__ img, int H, int W, TvConst tc, float* __restrict__ gtv,
+          float* __restrict__ tv_partials) {
+  __shared__ float s_red[8];
   const int y = blockIdx.y;
-  const int cg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = (blockIdx.x * 32 + lane) * 4;
+  const int x = blockIdx.x * 256 + threadIdx.x;
   float tv_local = 0.f;
-  if (x0 < W) {
-    float raw[3][3][6];
+  if (x < W) {
     const int ys[3] = {clampi(y - 1, 0, H - 1), y, clampi(y + 1, 0, H - 1)};
+    const int xs[3] = {clampi(x - 1, 0, W - 1), x, clampi(x + 1, 0, W - 1)};
+    const bool hasL = x > 0, hasR = x < W - 1, hasU = y > 0, hasD = y < H - 1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c) {
+      float n[3][3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float* row = img + ((size_t)c * H + ys[i]) * W;
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) raw[c][i][j] = __ldg(row + clampi(x0 - 1 + j, 0, W - 1));
+        for (int j = 0; j < 3; ++j) n[i][j] = __ldg(img + ((size_t)c * H + ys[i]) * W + xs[j]);
+      const float ctr = n[1][1];
+      // owned loss entries e1[y][x], e2[y][x], e3[y][x], e4[y][x] (+ extra row i=H / col j=W at the far borders)
+      const float e1 = n[1][2] - ctr, e2 = n[2][1] - ctr, e3 = ctr - n[0][0], e4 = n[1][0] - n[0][1];
+      float l = tc.l1 * (e1 * e1 + e2 * e2) + tc.l3 * (e3 * e3 + e4 * e4);
+      if (!hasD) { const float d = ctr - n[1][0]; l += tc.l3 * (d * d + d * d); }
+      if (!hasR) { const float d = ctr - n[0][1]; l += tc.l3 * (d * d + d * d); }
+      tv_local += l;
+      float g;
+      if (hasL && hasR && hasU && hasD) {
+        g = tc.k1 * (4.f * ctr - n[1][0] - n[1][2] - n[0][1] - n[2][1]) +
+            tc.k3 * (4.f * ctr - n[0][0] - n[2][2] - n[0][2] - n[2][0]);
+      } else {
+        const float* plane = img + (size_t)c * H * W;
+        g = 0.f;
+        for (int a = (hasU ? y + 1 : 0); a <= (hasD ? y + 1 : H + 1); ++a)
+          for (int b = (hasL ? x + 1 : 0); b <= (hasR ? x + 1 : W + 1); ++b)
+            g += tv_gpad_slow(plane, H, W, a, b, tc.k1, tc.k3);
       }
-    float acc[4][16];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[p][i] = s_b[cg * 16 + i];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        float nv[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) nv[j] = (raw[c][i][j] - c_mean[c]) / c_std[c];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float4* wp = reinterpret_cast<const float4*>(&s_w[((c * 3 + i) * 3 + j) * 64 + cg * 16]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wv = wp[q];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              acc[p][4 * q + 0] = fmaf(nv[p + j], wv.x, acc[p][4 * q + 0]);
-              acc[p][4 * q + 1] = fmaf(nv[p + j], wv.y, acc[p][4 * q + 1]);
-              acc[p][4 * q + 2] = fmaf(nv[p + j], wv.z, acc[p][4 * q + 2]);
-              acc[p][4 * q + 3] = fmaf(nv[p + j], wv.w, acc[p][4 * q + 3]);
-            }
-          }
-        }
-      }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (x0 + p < W) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(fmaxf(acc[p][2 * i], 0.f), fmaxf(acc[p][2 * i + 1], 0.f));
-        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * W + x0 + p) * 64 + cg * 16);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
-
-    if (do_tv && cg == 0) {  // warp-uniform: warp 0 also owns the TV loss / gradient of its 4 pixels x 3 channels
-      const bool hasU = y > 0, hasD = y < H - 1;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float gout[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int x = x0 + p;
-          gout[p] = 0.f;
-          if (x < W) {
-            // n[i][j] = raw[c][i][p + j]
-            const float ctr = raw[c][1][p + 1];
-            const float nL = raw[c][1][p], nR = raw[c][1][p + 2], nU = raw[c][0][p + 1], nDn = raw[c][2][p + 1];
-            const float nUL = raw[c][0][p], nUR = raw[c][0][p + 2], nDL = raw[c][2][p], nDR = raw[c][2][p + 2];
-            const bool hasL = x > 0, hasR = x < W - 1;
-            const float e1 = nR - ctr, e2 = nDn - ctr, e3 = ctr - nUL, e4 = nL - nU;
-            float l = tc.l1 * (e1 * e1 + e2 * e2) + tc.l3 * (e3 * e3 + e4 * e4);
-            if (!hasD) { const float d = ctr - nL; l += tc.l3 * (d * d + d * d); }   // extra row i = H
-            if (!hasR) { const float d = ctr - nU; l += tc.l3 * (d * d + d * d); }   // extra col j = W
-            tv_local += l;
-            float g;
-            if (hasL && hasR && hasU && hasD) {
-              g = tc.k1 * (4.f * ctr - nL - nR - nU - nDn) + tc.k3 * (4.f * ctr - nUL - nDR - nUR - nDL);
-            } else {
-              const float* plane = img + (size_t)c * H * W;
-              g = 0.f;
-              for (int a = (hasU ? y + 1 : 0); a <= (hasD ? y + 1 : H + 1); ++a)
-                for (int b = (hasL ? x + 1 : 0); b <= (hasR ? x + 1 : W + 1); ++b)
-                  g += tv_gpad_slow(plane, H, W, a, b, tc.k1, tc.k3);
-            }
-            gout[p] = g;
-          }
-        }
-        float* gp = gtv + ((size_t)c * H + y) * W + x0;
-        if ((W & 3) == 0) {
-          *reinterpret_cast<float4*>(gp) = make_float4(gout[0], gout[1], gout[2], gout[3]);
-        } else {
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (x0 + p < W) gp[p] = gout[p];
-        }
-      }
+      gtv[((size_t)c * H + y) * W + x] = g;
     }
   }
-  if (do_tv && cg == 0) {
-    const float sum = warp_sum(tv_local);
-    if (lane == 0) tv_partials[blockIdx.y * gridDim.x + blockIdx.x] = sum;
+  float sum = warp_sum(tv_local);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    tv_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// conv0 forward, tensor-core path, step 1: im2col of the normalised, replicate-padded image into a pixel-major bf16
+// operand [H][W][64]: k < 27 the bf16 "hi" part of the 27 taps (k = (c*3+ky)*3+kx), 27 <= k < 54 the bf16 residual
+// ("lo", so the pair carries 16 mantissa bits), rest zero.  Step 2 is a 1x1 pixel-GEMM against [64][64] weights
+// laid out the same way, with conv0's bias and ReLU in its epilogue.
+// 8 lanes per pixel, lane `sub` produces the 16-byte chunk k = 8*sub .. 8*sub+7 (fully coalesced 128-byte rows).
+__global__ void __launch_bounds__(256)
+im2col0_kernel(const float* __restrict__ img, bf16* __restrict__ out, int H, int W) {
+  const long t = (long)blockIdx.x * 256 + threadIdx.x;
+  const long pix = t >> 3;
+  const int sub = (int)(t & 7);
+  if (pix >= (long)H * W) return;
+  const int y = (int)(pix / W), x = (int)(pix % W);
+  const float inv_std[3] = {(float)(1.0 / 0.229), (float)(1.0 / 0.224), (float)(1.0 / 0.225)};
+  float v8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = sub * 8 + e;
+    float val = 0.f;
+    if (k < 54) {
+      const int tap = k < 27 ? k : k - 27;
+      const int c = tap / 9, i = (tap % 9) / 3, j = tap % 3;
+      const float v = (__ldg(img + ((size_t)c * H + clampi(y + i - 1, 0, H - 1)) * W + clampi(x + j - 1, 0, W - 1)) -
+                       c_mean[c]) * inv_std[c];
+      const float h = __bfloat162float(__float2bfloat16(v));
+      val = k < 27 ? h : v - h;
+    }
+    v8[e] = val;
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + sub * 8) =
+      make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
+                 pack_bf16x2(v8[6], v8[7]));
+}
+
+__global__ void pack_w0_fwd_kernel(const float* __restrict__ w0, bf16* __restrict__ out) {
+  // out[n][k]: k < 27 -> w0[n][k]; 27 <= k < 54 -> w0[n][k-27]; else 0
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 64) {
+    const int n = i >> 6, k = i & 63;
+    out[i] = __float2bfloat16(k < 27 ? w0[n * 27 + k] : (k < 54 ? w0[n * 27 + k - 27] : 0.f));
   }
 }
 
 // ------------------------------------------------------------------------------------------------ conv0 bwd + Adam
-// One warp = a strip of 32 consecutive pixels of one row.  Lanes are CHANNELS (lane l owns g0 channels 2l, 2l+1 and
-// keeps their 2 x 27 weights in registers); the strip is walked pixel by pixel with a sliding 3x3 window of
-// coalesced 128-byte loads (3 new loads per step), the three image-channel sums are butterfly-reduced and parked
-// on lane p; afterwards lane p applies Normalize-backward + TV gradient + Adam + clamp + EMA to pixel p (coalesced).
+// Persistent warps; one work item = a strip of 32 consecutive pixels of one row.  Lanes are CHANNELS (lane l owns g0
+// channels 2l, 2l+1 and keeps their 2 x 27 weights in registers for the whole kernel); the strip is walked pixel by
+// pixel with a sliding 3x3 window of coalesced 128-byte loads (the next column is prefetched before the current
+// pixel's math), the three image-channel sums are butterfly-reduced and parked on lane p; afterwards lane p applies
+// Normalize-backward + TV gradient + Adam + clamp + EMA to pixel p (coalesced).
 struct F2 { float x, y; };
 
 __global__ void __launch_bounds__(256)
-conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const float* __restrict__ w0, const float* __restrict__ gtv,
-                      float* __restrict__ img, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                      float* __restrict__ ema, float* __restrict__ grad_out, int H, int W, AdamScalars ac,
-                      int apply_update) {
+conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint, const float* __restrict__ w0,
+                      const float* __restrict__ gtv, float* __restrict__ img, float* __restrict__ exp_avg,
+                      float* __restrict__ exp_avg_sq, float* __restrict__ ema, float* __restrict__ grad_out, int H,
+                      int W, AdamScalars ac, int apply_update) {
+  __shared__ float s_w[64 * 27];
+  for (int i = threadIdx.x; i < 64 * 27; i += 256) s_w[i] = w0[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int strips = (W + 31) >> 5;
-  const long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wg >= (long)H * strips) return;
-  const int y = (int)(wg / strips);
-  const int xs = (int)(wg % strips) * 32;
+  const long total = (long)H * strips;
+  const long nwarps = (long)gridDim.x * 8;
   const uint32_t* __restrict__ g32 = reinterpret_cast<const uint32_t*>(g0);
 
   // wr[tap][c]: weights of this lane's two channels; tap = ky*3+kx
@@ -195,93 +172,106 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const float* __restrict__ w0,
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      wr[t][c].x = __ldg(w0 + ((2 * lane) * 3 + c) * 9 + t);
-      wr[t][c].y = __ldg(w0 + ((2 * lane + 1) * 3 + c) * 9 + t);
+      wr[t][c].x = s_w[((2 * lane) * 3 + c) * 9 + t];
+      wr[t][c].y = s_w[((2 * lane + 1) * 3 + c) * 9 + t];
     }
 
-  auto ld = [&](int yo, int xo) -> F2 {
-    F2 r{0.f, 0.f};
-    if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
-      const uint32_t u = __ldg(g32 + ((size_t)yo * W + xo) * 32 + lane);
-      r.x = bf16lo(u);
-      r.y = bf16hi(u);
-    }
-    return r;
-  };
-
-  float keep[3] = {0.f, 0.f, 0.f};
-  F2 win[3][3];
-  bool have = false;
-  const bool row_interior = (y > 0) && (y < H - 1);
-  const int xe = min(xs + 32, W);
-  for (int x = xs; x < xe; ++x) {
-    float acc[3] = {0.f, 0.f, 0.f};
-    if (row_interior && x > 0 && x < W - 1) {
-      if (have) {
+  for (long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5); wg < total; wg += nwarps) {
+    const int y = (int)(wg / strips);
+    const int xs = (int)(wg % strips) * 32;
+    auto ld = [&](int yo, int xo) -> F2 {
+      F2 r{0.f, 0.f};
+      if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
+        const uint32_t u = __ldg(g32 + ((size_t)yo * W + xo) * 32 + lane);
+        r.x = bf16lo(u);
+        r.y = bf16hi(u);
+      }
+      return r;
+    };
+    float keep[3] = {0.f, 0.f, 0.f};
+    F2 win[3][3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { win[r][0] = win[r][1]; win[r][1] = win[r][2]; win[r][2] = ld(y - 1 + r, x + 1); }
-      } else {
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx)
+        win[r][cidx] = (gint == nullptr) ? ld(y - 1 + r, xs - 1 + cidx) : F2{0.f, 0.f};
+    const bool row_interior = (y > 0) && (y < H - 1);
+    const int xe = min(xs + 32, W);
+    // gint != nullptr: the zero-pad dgrad of the interior pixels was already computed on the tensor cores
+    // (pixel_gemm with conv0's weights zero-padded to 64 output channels); only border pixels (where replicate
+    // padding folds extra taps onto the pixel) are evaluated here.
+    const bool strip_has_border = !row_interior || xs == 0 || xe == W;
+    if (gint == nullptr || strip_has_border)
+    for (int x = xs; x < xe; ++x) {
+      if (gint != nullptr && row_interior && x > 0 && x < W - 1) continue;
+      F2 nxt[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) nxt[r] = ld(y - 1 + r, x + 2);  // prefetch the next window column
+      float acc[3] = {0.f, 0.f, 0.f};
+      if (row_interior && x > 0 && x < W - 1) {
+        // padded position (y+1, x+1): g0[y+1-ky][x+1-kx] <-> win[2-ky][2-kx]
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int cidx = 0; cidx < 3; ++cidx) win[r][cidx] = ld(y - 1 + r, x - 1 + cidx);
-        have = true;
-      }
-      // padded position (y+1, x+1): g0[y+1-ky][x+1-kx] <-> win[2-ky][2-kx]
+          for (int cidx = 0; cidx < 3; ++cidx) {
+            const int t = (2 - r) * 3 + (2 - cidx);
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cidx = 0; cidx < 3; ++cidx) {
-          const int t = (2 - r) * 3 + (2 - cidx);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            acc[c] = fmaf(win[r][cidx].x, wr[t][c].x, acc[c]);
-            acc[c] = fmaf(win[r][cidx].y, wr[t][c].y, acc[c]);
-          }
-        }
-    } else {
-      // border pixel: sum over the padded positions that replicate-padding folds onto it (warp-uniform branch)
-      have = false;
-      const int a0 = (y == 0) ? 0 : y + 1, a1 = (y == H - 1) ? H + 1 : y + 1;
-      const int b0 = (x == 0) ? 0 : x + 1, b1 = (x == W - 1) ? W + 1 : x + 1;
-      for (int a = a0; a <= a1; ++a)
-        for (int b = b0; b <= b1; ++b)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const F2 v = ld(a - ky, b - kx);
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                acc[c] = fmaf(v.x, wr[ky * 3 + kx][c].x, acc[c]);
-                acc[c] = fmaf(v.y, wr[ky * 3 + kx][c].y, acc[c]);
-              }
+            for (int c = 0; c < 3; ++c) {
+              acc[c] = fmaf(win[r][cidx].x, wr[t][c].x, acc[c]);
+              acc[c] = fmaf(win[r][cidx].y, wr[t][c].y, acc[c]);
             }
-    }
+          }
+      } else {
+        // border pixel: sum over the padded positions that replicate-padding folds onto it (warp-uniform branch)
+        const int a0 = (y == 0) ? 0 : y + 1, a1 = (y == H - 1) ? H + 1 : y + 1;
+        const int b0 = (x == 0) ? 0 : x + 1, b1 = (x == W - 1) ? W + 1 : x + 1;
+        for (int a = a0; a <= a1; ++a)
+          for (int b = b0; b <= b1; ++b)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+              for (int kx = 0; kx < 3; ++kx) {
+                const F2 v = ld(a - ky, b - kx);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  acc[c] = fmaf(v.x, wr[ky * 3 + kx][c].x, acc[c]);
+                  acc[c] = fmaf(v.y, wr[ky * 3 + kx][c].y, acc[c]);
+                }
+              }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+      }
+      if (lane == x - xs) { keep[0] = acc[0]; keep[1] = acc[1]; keep[2] = acc[2]; }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { win[r][0] = win[r][1]; win[r][1] = win[r][2]; win[r][2] = nxt[r]; }
     }
-    if (lane == x - xs) { keep[0] = acc[0]; keep[1] = acc[1]; keep[2] = acc[2]; }
-  }
 
-  const int x = xs + lane;
-  if (x < W) {
+    const int x = xs + lane;
+    if (x < W) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const size_t idx = ((size_t)c * H + y) * W + x;
-      const float g = keep[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
-      if (grad_out) grad_out[idx] = g;
-      if (apply_update) {
-        float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
-        m = m + (g - m) * ac.one_minus_b1;
-        v = v * ac.b2 + ac.one_minus_b2 * g * g;
-        const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
-        p = p - ac.step_size * (m / denom);
-        p = fminf(fmaxf(p, 0.f), 1.f);
-        e = e * ac.ema_decay + ac.one_minus_decay * p;
-        exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+      const bool from_tc = gint != nullptr && row_interior && x > 0 && x < W - 1;
+      float tcg[3] = {0.f, 0.f, 0.f};
+      if (from_tc) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(gint + ((size_t)y * W + x) * 64));
+        tcg[0] = bf16lo(u.x); tcg[1] = bf16hi(u.x); tcg[2] = bf16lo(u.y);
+      }
+      for (int c = 0; c < 3; ++c) {
+        const size_t idx = ((size_t)c * H + y) * W + x;
+        const float g = (from_tc ? tcg[c] : keep[c]) / c_std[c] + (gtv ? gtv[idx] : 0.f);
+        if (grad_out) grad_out[idx] = g;
+        if (apply_update) {
+          float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
+          m = m + (g - m) * ac.one_minus_b1;
+          v = v * ac.b2 + ac.one_minus_b2 * g * g;
+          const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
+          p = p - ac.step_size * (m / denom);
+          p = fminf(fmaxf(p, 0.f), 1.f);
+          e = e * ac.ema_decay + ac.one_minus_decay * p;
+          exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+        }
       }
     }
   }
@@ -434,30 +424,42 @@ sse_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long n8, floa
 }  // namespace
 
 // ================================================================================================ launchers
-int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* out, int H, int W, float tv_weight,
-                     float* gtv, float* tv_partials, int* n_partials, cudaStream_t s) {
-  dim3 grid((W + 127) / 128, H);
+int launch_tv(const float* img, int H, int W, float tv_weight, float* gtv, float* tv_partials, int* n_partials,
+              cudaStream_t s) {
   TvConst tc{};
-  const int do_tv = gtv != nullptr;
-  if (do_tv) {
-    const double n1 = 3.0 * H * W, n3 = 3.0 * (H + 1.0) * (W + 1.0);
-    tc.k1 = (float)(tv_weight * 4.0 / (3.0 * n1));
-    tc.k3 = (float)(tv_weight * 4.0 / (12.0 * n3));
-    tc.l1 = (float)(2.0 / (3.0 * n1));
-    tc.l3 = (float)(2.0 / (12.0 * n3));
-  }
-  if (n_partials) *n_partials = grid.x * grid.y;
-  conv0_fwd_tv_kernel<<<grid, 128, 0, s>>>(img, w0, b0, out, H, W, do_tv, tc, gtv, tv_partials);
+  const double n1 = 3.0 * H * W, n3 = 3.0 * (H + 1.0) * (W + 1.0);
+  tc.k1 = (float)(tv_weight * 4.0 / (3.0 * n1));
+  tc.k3 = (float)(tv_weight * 4.0 / (12.0 * n3));
+  tc.l1 = (float)(2.0 / (3.0 * n1));
+  tc.l3 = (float)(2.0 / (12.0 * n3));
+  dim3 tgrid((W + 255) / 256, H);
+  if (n_partials) *n_partials = tgrid.x * tgrid.y;
+  tv_kernel<<<tgrid, 256, 0, s>>>(img, H, W, tc, gtv, tv_partials);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
 
-int launch_conv0_bwd_adam(const bf16* g0, const float* w0, const float* gtv, float* img, float* exp_avg,
-                          float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars& a,
-                          int apply_update, cudaStream_t s) {
+int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s) {
+  const long threads = (long)H * W * 8;
+  im2col0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(img, out, H, W);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s) {
+  pack_w0_fwd_kernel<<<16, 256, 0, s>>>(w0, out);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
+                          float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
+                          const AdamScalars& a, int apply_update, cudaStream_t s) {
   const long warps = (long)H * ((W + 31) / 32);
-  const int blocks = (int)((warps + 7) / 8);
-  conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a,
+  long want = (warps + 7) / 8;
+  const long cap = (long)num_sms() * 2 * 4;  // persistent: a few waves of 8-warp CTAs
+  const int blocks = (int)(want < cap ? want : cap);
+  conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, gint, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a,
                                                apply_update);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;

@@ -45,13 +45,20 @@ int pack_weights_bwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t 
 struct AdamScalars {  // torch/optim/adam.py:413-546 scalars, evaluated on the host in double like torch does
   float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps, ema_decay, one_minus_decay;
 };
-// gtv == nullptr: features-only forward (no TV).  tv_partials gets one float per CTA (n_partials of them).
-int launch_conv0_fwd(const float* img, const float* w0, const float* b0, bf16* out, int H, int W, float tv_weight,
-                     float* gtv, float* tv_partials, int* n_partials, cudaStream_t s);
-// g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  grad_out (optional) receives d loss/d image.
-int launch_conv0_bwd_adam(const bf16* g0, const float* w0, const float* gtv, float* img, float* exp_avg,
-                          float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars& a,
-                          int apply_update, cudaStream_t s);
+// TV loss partials + gradient (times tv_weight) on the raw image; im2col of the normalised replicate-padded image
+// for the tensor-core conv0 ([H][W][64] bf16: 27 hi taps, 27 lo residuals, 10 zeros) and the matching weights.
+int launch_tv(const float* img, int H, int W, float tv_weight, float* gtv, float* tv_partials, int* n_partials,
+              cudaStream_t s);
+int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s);
+int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s);
+// g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  gint (optional): zero-pad dgrad of g0
+// through conv0 computed on the tensor cores, bf16 NHWC [H][W][64] with channels 0..2 valid (interior pixels are
+// taken from it, border pixels are evaluated here).  grad_out (optional) receives d loss/d image.
+int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
+                          float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
+                          const AdamScalars& a, int apply_update, cudaStream_t s);
+// conv0 dgrad weights for the tensor-core path: fp32 OIHW [64][3][3][3] -> bf16 [9][64 (ci, 3 real)][64 (co)]
+int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s);
 int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s);
 int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s);
 int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s);
@@ -68,6 +75,7 @@ struct GemmProb {  // D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd +
   float* D;
   float* red_out;  // optional: per-tile {sum of squares, trace} of D, [ (n/64)^2 ][2]
   int n, transA, transB, transA2, transB2;
+  int sym;  // result is symmetric: compute tiles ti <= tj only and mirror them
   float alpha, alpha2, beta, gamma;
 };
 enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };

@@ -5,8 +5,9 @@
 // plus the closed-form backward of ST:163-181 down to  G = d loss / d srm  and  d loss / d mean.
 //
 // The loss is a cancellation (tr(St + S - 2 sqrt(.))): TF32/bf16 operands are not accurate
-// enough, so these C x C chains run on the FP32 FMA pipe.  All five layers advance in lock-step: one "round" = one
-// grouped launch whose CTAs are 64x64 tiles of every layer's GEMM (1+4+16+64+64 = 149 tiles ~ one wave of 148 SMs).
+// enough, so these C x C chains are evaluated with fp32 operands and an error-compensated 3xTF32 split on the tensor
+// cores (fp32-level accuracy).  All five layers advance in lock-step: one "round" = one grouped launch whose CTAs are
+// 64x64 tiles of every layer's GEMM.
 #include <vector>
 
 #include "kernels.h"
@@ -21,10 +22,31 @@ constexpr int KC = 8;      // k chunk per smem stage
 constexpr int KG = 8;      // in-CTA split-K groups (64 threads each) -> 512 threads
 constexpr int NRED = 64;   // max reduction partials per layer (tiles of a 512x512 problem / helper CTAs)
 
-// D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I on 64x64 tiles.  One CTA = 8 k-groups x 64
-// threads; a group owns 1/8 of K with private smem double buffers and 8x8 register tiles (FMA:LDS = 16:1), the
-// groups' partial tiles are tree-reduced through smem, group 0 applies the epilogue.  Optionally writes the tile's
-// {sum of squares, trace} partial for the Frobenius norms of the Newton-Schulz chain (deterministic order).
+// D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I on 64x64 tiles, fp32 in / fp32 out.
+//
+// The products run on the tensor cores with an error-compensated 3xTF32 split done in registers:
+//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly representable in TF32),  lo = x - hi,
+//     a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b          (the dropped lo*lo term is 2^-22 relative),
+// accumulated in fp32 (mma.sync.m16n8k8.tf32).  Plain TF32 is NOT accurate enough for this chain;
+// the split restores fp32-level accuracy (tests/test_gpu_kernels.py::test_w2_*).
+//
+// One CTA = 8 k-groups x 2 warps: a group owns 1/8 of K with private smem double buffers; warp w of a group owns
+// rows [32w, 32w+32) of the tile as 2 x 8 m16n8 fragments.  The groups' partial tiles are tree-reduced through
+// smem, group 0 applies the epilogue.  Symmetric results are computed for tiles ti <= tj only and mirrored.
+// Optionally writes the tile's {sum of squares, trace} partial for the Newton-Schulz norms (deterministic order).
+constexpr int LDT = TS + 8;  // smem row stride (floats): fragment loads hit 32 distinct banks
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 __global__ void __launch_bounds__(KG * 64, 1)
 sgemm_grouped_kernel(const GemmProb* __restrict__ probs, const uint32_t* __restrict__ tiles) {
   extern __shared__ __align__(16) float smem_f[];
@@ -33,14 +55,17 @@ sgemm_grouped_kernel(const GemmProb* __restrict__ probs, const uint32_t* __restr
   const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
   const int n = pr.n;
   const int grp = threadIdx.x >> 6, lt = threadIdx.x & 63;
-  const int tx = lt & 7, ty = lt >> 3;
-  float* As = smem_f + grp * (4 * KC * TS);  // [2][KC][TS]
-  float* Bs = As + 2 * KC * TS;              // [2][KC][TS]
-  float acc[8][8];
+  const int w2 = lt >> 5, lane = lt & 31, g = lane >> 2, tq = lane & 3;
+  float* As = smem_f + grp * (4 * KC * LDT);  // [2][KC][LDT]
+  float* Bs = As + 2 * KC * LDT;              // [2][KC][LDT]
+  // acc[mi][ni][r]: rows 32*w2 + 16*mi + g (+8 for r >= 2), cols 8*ni + 2*tq + (r & 1)
+  float acc[2][8][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.f;
 
   const int kper = n / KG;           // k range of this group (n is a multiple of 64)
   const int kbeg = grp * kper;
@@ -68,26 +93,26 @@ sgemm_grouped_kernel(const GemmProb* __restrict__ probs, const uint32_t* __restr
       }
     };
     auto sstore = [&](int buf) {
-      float* a = As + buf * KC * TS;
-      float* b = Bs + buf * KC * TS;
+      float* a = As + buf * KC * LDT;
+      float* b = Bs + buf * KC * LDT;
       const float av[8] = {ra[0].x * alpha, ra[0].y * alpha, ra[0].z * alpha, ra[0].w * alpha,
                            ra[1].x * alpha, ra[1].y * alpha, ra[1].z * alpha, ra[1].w * alpha};
       const float bv[8] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w, rb[1].x, rb[1].y, rb[1].z, rb[1].w};
       if (!tA) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a[k * TS + lt] = av[k];
+        for (int k = 0; k < 8; ++k) a[k * LDT + lt] = av[k];
       } else {
-        float4* d = reinterpret_cast<float4*>(a + (lt >> 3) * TS + (lt & 7) * 8);
+        float4* d = reinterpret_cast<float4*>(a + (lt >> 3) * LDT + (lt & 7) * 8);
         d[0] = make_float4(av[0], av[1], av[2], av[3]);
         d[1] = make_float4(av[4], av[5], av[6], av[7]);
       }
       if (!tB) {
-        float4* d = reinterpret_cast<float4*>(b + (lt >> 3) * TS + (lt & 7) * 8);
+        float4* d = reinterpret_cast<float4*>(b + (lt >> 3) * LDT + (lt & 7) * 8);
         d[0] = make_float4(bv[0], bv[1], bv[2], bv[3]);
         d[1] = make_float4(bv[4], bv[5], bv[6], bv[7]);
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) b[k * TS + lt] = bv[k];
+        for (int k = 0; k < 8; ++k) b[k * LDT + lt] = bv[k];
       }
     };
     gload(kbeg);
@@ -97,89 +122,112 @@ sgemm_grouped_kernel(const GemmProb* __restrict__ probs, const uint32_t* __restr
     for (int k0 = 0; k0 < kper; k0 += KC) {
       const bool more = (k0 + KC) < kper;
       if (more) gload(kbeg + k0 + KC);
-      const float* a = As + buf * KC * TS;
-      const float* b = Bs + buf * KC * TS;
+      const float* a = As + buf * KC * LDT;
+      const float* b = Bs + buf * KC * LDT;
+      // one m16n8k8 k-step per chunk (KC == 8)
+      uint32_t ah[2][4], al[2][4];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(a + k * TS + ty * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(a + k * TS + ty * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(b + k * TS + tx * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(b + k * TS + tx * 8 + 4);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int mi = 0; mi < 2; ++mi) {
+        const int rb_ = w2 * 32 + mi * 16 + g;
+        split_tf32(a[tq * LDT + rb_], ah[mi][0], al[mi][0]);
+        split_tf32(a[tq * LDT + rb_ + 8], ah[mi][1], al[mi][1]);
+        split_tf32(a[(tq + 4) * LDT + rb_], ah[mi][2], al[mi][2]);
+        split_tf32(a[(tq + 4) * LDT + rb_ + 8], ah[mi][3], al[mi][3]);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+      for (int ni = 0; ni < 8; ++ni) {
+        uint32_t bh[2], bl[2];
+        split_tf32(b[tq * LDT + ni * 8 + g], bh[0], bl[0]);
+        split_tf32(b[(tq + 4) * LDT + ni * 8 + g], bh[1], bl[1]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int mi = 0; mi < 2; ++mi) {
+          mma_tf32(acc[mi][ni], al[mi], bh);
+          mma_tf32(acc[mi][ni], ah[mi], bl);
+          mma_tf32(acc[mi][ni], ah[mi], bh);
+        }
       }
       if (more) sstore(buf ^ 1);
       named_bar_sync(1 + grp, 64);
       buf ^= 1;
     }
   }
-  // ---- tree reduction of the 8 partial tiles through smem (reuses the staging buffers: 8 x 16 KiB)
+  // ---- tree reduction of the 8 partial tiles through smem (reuses the staging buffers)
   __syncthreads();
-  float* red = smem_f;  // [4][64 threads][64] floats max
+  float* red = smem_f;  // [4][64 threads][64] floats
+  float* accf = &acc[0][0][0];
   for (int half = KG / 2; half >= 1; half >>= 1) {
     if (grp >= half && grp < 2 * half) {
       float* dst = red + ((grp - half) * 64 + lt) * 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; j += 4)
-          *reinterpret_cast<float4*>(dst + ((i * 8 + j) ^ ((lt & 7) * 4))) =
-              make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      for (int e = 0; e < 64; e += 4)
+        *reinterpret_cast<float4*>(dst + (e ^ ((lt & 7) * 4))) = make_float4(accf[e], accf[e + 1], accf[e + 2], accf[e + 3]);
     }
     __syncthreads();
     if (grp < half) {
       const float* src = red + (grp * 64 + lt) * 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(src + ((i * 8 + j) ^ ((lt & 7) * 4)));
-          acc[i][j] += v.x; acc[i][j + 1] += v.y; acc[i][j + 2] += v.z; acc[i][j + 3] += v.w;
-        }
+      for (int e = 0; e < 64; e += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (e ^ ((lt & 7) * 4)));
+        accf[e] += v.x; accf[e + 1] += v.y; accf[e + 2] += v.z; accf[e + 3] += v.w;
+      }
     }
     __syncthreads();
   }
   if (grp == 0) {
     float ssq = 0.f, tr = 0.f;
+    const bool mirror = pr.sym && ti != tj;
+    float* tp = smem_f + 4096;  // [64][65] transpose buffer inside the idle staging area
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gi = ti * TS + ty * 8 + i;
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int j4 = 0; j4 < 8; j4 += 4) {
-        const int gj = tj * TS + tx * 8 + j4;
-        float4 o = make_float4(acc[i][j4], acc[i][j4 + 1], acc[i][j4 + 2], acc[i][j4 + 3]);
-        if (pr.Cadd != nullptr) {
-          const float4 c = *reinterpret_cast<const float4*>(pr.Cadd + (size_t)gi * n + gj);
-          o.x = fmaf(pr.beta, c.x, o.x); o.y = fmaf(pr.beta, c.y, o.y);
-          o.z = fmaf(pr.beta, c.z, o.z); o.w = fmaf(pr.beta, c.w, o.w);
+      for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int lr = w2 * 32 + mi * 16 + g + h * 8, lc = ni * 8 + 2 * tq;  // local row / col of (c[2h], c[2h+1])
+          const int gi = ti * TS + lr, gj = tj * TS + lc;
+          float2 o = make_float2(acc[mi][ni][2 * h], acc[mi][ni][2 * h + 1]);
+          if (pr.Cadd != nullptr) {
+            const float2 c = *reinterpret_cast<const float2*>(pr.Cadd + (size_t)gi * n + gj);
+            o.x = fmaf(pr.beta, c.x, o.x);
+            o.y = fmaf(pr.beta, c.y, o.y);
+          }
+          if (gi == gj) { o.x += pr.gamma; tr += o.x; }
+          if (gi == gj + 1) { o.y += pr.gamma; tr += o.y; }
+          ssq = fmaf(o.x, o.x, ssq);
+          ssq = fmaf(o.y, o.y, ssq);
+          *reinterpret_cast<float2*>(pr.D + (size_t)gi * n + gj) = o;
+          if (mirror) { tp[lc * 65 + lr] = o.x; tp[(lc + 1) * 65 + lr] = o.y; }
         }
-        if (gi >= gj && gi < gj + 4) {
-          (&o.x)[gi - gj] += pr.gamma;
-          tr += (&o.x)[gi - gj];
-        }
-        ssq = fmaf(o.x, o.x, ssq); ssq = fmaf(o.y, o.y, ssq); ssq = fmaf(o.z, o.z, ssq); ssq = fmaf(o.w, o.w, ssq);
-        *reinterpret_cast<float4*>(pr.D + (size_t)gi * n + gj) = o;
-      }
+    if (mirror) {
+      // symmetric result (product of commuting symmetric matrices): the mirror tile D[tj][ti] = tile^T is written
+      // through the padded smem transpose (thread lt writes row lt, coalesced float4)
+      ssq *= 2.f;
+      named_bar_sync(1, 64);
+      float* drow = pr.D + (size_t)(tj * TS + lt) * n + ti * TS;
+#pragma unroll
+      for (int c4 = 0; c4 < 64; c4 += 4)
+        *reinterpret_cast<float4*>(drow + c4) =
+            make_float4(tp[lt * 65 + c4], tp[lt * 65 + c4 + 1], tp[lt * 65 + c4 + 2], tp[lt * 65 + c4 + 3]);
     }
-    if (pr.red_out != nullptr) {  // warp-uniform: grp 0 = warps 0,1
+    if (pr.red_out != nullptr) {  // warp-uniform: group 0 = warps 0, 1
       ssq = warp_sum(ssq);
       tr = warp_sum(tr);
-      float* sh = smem_f + 8192;  // beyond the region read above by group 0? (all reads done: safe after barrier)
+      float* sh = smem_f + 12288;  // scratch inside the idle staging area (disjoint from the transpose buffer)
       if ((lt & 31) == 0) { sh[(lt >> 5) * 2] = ssq; sh[(lt >> 5) * 2 + 1] = tr; }
       named_bar_sync(1, 64);
       if (lt == 0) {
         const int nt = n / TS;
         pr.red_out[(ti * nt + tj) * 2] = sh[0] + sh[2];
         pr.red_out[(ti * nt + tj) * 2 + 1] = sh[1] + sh[3];
+        if (mirror) {  // consumers sum all (n/64)^2 slots: the mirror tile's share is already doubled above
+          pr.red_out[(tj * nt + ti) * 2] = 0.f;
+          pr.red_out[(tj * nt + ti) * 2 + 1] = 0.f;
+        }
       }
     }
   }
 }
-constexpr int SGEMM_SMEM = KG * 4 * KC * TS * 4;  // 64 KiB
+constexpr int SGEMM_SMEM = KG * 4 * KC * LDT * 4;  // 72 KiB (>= the 64 KiB the tree reduction needs)
 
 // ---- helpers: grid (5 layers, NB CTAs), 256 threads; reductions via fixed-order partials (deterministic)
 constexpr int NB = 32;
@@ -335,14 +383,15 @@ static void add_prob(std::vector<GemmProb>& probs, std::vector<uint32_t>& tiles,
   probs.push_back(p);
   const int nt = p.n / TS;
   for (int i = 0; i < nt; ++i)
-    for (int j = 0; j < nt; ++j) tiles.push_back((uint32_t)idx << 16 | (uint32_t)i << 8 | (uint32_t)j);
+    for (int j = (p.sym ? i : 0); j < nt; ++j) tiles.push_back((uint32_t)idx << 16 | (uint32_t)i << 8 | (uint32_t)j);
 }
 
 static GemmProb mk(int n, float* D, const float* A, int tA, const float* B, int tB, float alpha, float gamma = 0.f,
                    const float* Cadd = nullptr, float beta = 0.f, const float* A2 = nullptr, int tA2 = 0,
-                   const float* B2 = nullptr, int tB2 = 0, float alpha2 = 0.f, float* red_out = nullptr) {
+                   const float* B2 = nullptr, int tB2 = 0, float alpha2 = 0.f, float* red_out = nullptr, int sym = 1) {
   GemmProb p{};
   p.red_out = red_out;
+  p.sym = sym;
   p.A = A; p.B = B; p.A2 = A2; p.B2 = B2; p.Cadd = Cadd; p.D = D; p.n = n;
   p.transA = tA; p.transB = tB; p.transA2 = tA2; p.transB2 = tB2;
   p.alpha = alpha; p.alpha2 = alpha2; p.beta = beta; p.gamma = gamma;
@@ -407,7 +456,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   // (b) iterate forward: X = P cov; M = X P; NS
   r_fwd_begin = (int)rounds.size();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.X, L.P, 0, L.cov, 0, 1.f)); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.X, L.P, 0, L.cov, 0, 1.f, 0.f, nullptr, 0.f, nullptr, 0, nullptr, 0, 0.f, nullptr, 0)); }
   end_round();
   begin_round();
   for (int l = 0; l < 5; ++l) {
@@ -438,7 +487,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   }
   // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I  (gamma patched per layer in set_weights)
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.U, L.P, 1, L.Q[0], 0, 1.f)); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; add_prob(probs, tiles, mk(L.n, L.U, L.P, 1, L.Q[0], 0, 1.f, 0.f, nullptr, 0.f, nullptr, 0, nullptr, 0, 0.f, nullptr, 0)); }
   end_round();
   begin_round();
   gc_prob_first = (int)probs.size();
