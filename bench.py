@@ -18,8 +18,9 @@ native arm   value   = it/s of K stb_iterate calls, state resident in HBM, CUDA 
              cpu_baseline = the oracle port (same torch-CPU primitives the reference's CPU path uses) timed on the
                        host cores on a bounded sample, extrapolated with an affine cost model in pixels.
 reference arm (--impl reference): the CPU baseline alone, printed in the same JSON shape.
-N > 1: independent replicas of the single-GPU job (weak scaling, no data-path collective); spatial tiling with
-halo aprons is the next step and will replace this.
+N > 1: ONE 2048x2048 job tiled spatially over the N GPUs (strong scaling): horizontal bands with 80-row halo aprons,
+one NCCL all-reduce of the 2.4 MB statistics block, a seam exchange of the image gradient and a halo refresh of the
+image per iteration (style-transfer-pytorch_b200/distributed.py).
 """
 import argparse
 import json
@@ -139,7 +140,7 @@ def run_reference(args, rank, world):
     cb = cpu_baseline(args.size, budget_s=60.0)
     line = dict(metric='stylize iterations/sec at end_scale=2048', value=cb['value'], unit='it/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / cb['value'], higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                scaling='strong', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'{args.size}x{args.size} single scale, pooling=max, content+1 style, '
                                      'CPU reference path (oracle port of stylize() loop body)'),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit='it/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -162,18 +163,34 @@ def run_native(args, rank, local_rank, world):
     size = args.size
     wts = O.make_vgg_weights(1234)
     content, style = O.synth_image(1, 16, size, size), O.synth_image(2, 32, size, size)
+    from style_transfer_b200 import distributed as D
     st = stb.StyleTransfer(devices=[str(dev)], pooling='max', vgg_weights=wts)
     m = st.model
-    m.ensure_workspace([(size, size)])
+    band = D.make_band(size, rank, world) if world > 1 else None
+    h_loc = band.h_local if band is not None else size
+    m.ensure_workspace([(h_loc, size), (size, size)])
     cimg = O.to_tensor(content).to(dev)
     simg = O.to_tensor(style).to(dev)
-    ct = m.content_features(cimg)
     means, srms = m.style_stats(simg)
-    m.set_targets(size, size, ct, 0.015, means, srms, st.style_weights, 2.0)
+    if band is not None:
+        cimg = D.local_slice(cimg, band)
+        m.set_band(True, size, band.own0, band.own_rows)
+    ct = m.content_features(cimg)
+    m.set_targets(h_loc, size, ct, 0.015, means, srms, st.style_weights, 2.0)
     st.image = cimg.clone()
     st.average = stb.style_transfer.EMA(st.image, 0.99)
     ea, eas = torch.zeros_like(st.image), torch.zeros_like(st.image)
     step = 0
+    if band is not None:
+        stats, grad = m.stats_view(h_loc, size), torch.empty_like(st.image)
+
+    def one_iteration():
+        nonlocal step
+        step += 1
+        if band is not None:
+            st._iterate_banded(band, stats, grad, ea, eas, step, 0.02, 0.99)
+        else:
+            st._iterate(ea, eas, step, 0.02, 0.99, True)
 
     def barrier():
         if world > 1:
@@ -181,8 +198,7 @@ def run_native(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step += 1
-        st._iterate(ea, eas, step, 0.02, 0.99, True)
+        one_iteration()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -191,8 +207,7 @@ def run_native(args, rank, local_rank, world):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step += 1
-        st._iterate(ea, eas, step, 0.02, 0.99, True)
+        one_iteration()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -203,7 +218,9 @@ def run_native(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * args.steps / (ms_total / 1000.0)  # replicas: every rank ran `steps` iterations of its own job
+    tiled = band is not None
+    # tiled: all ranks advanced ONE job by `steps` iterations; otherwise (N == 1) the single job
+    value = args.steps / (ms_total / 1000.0)
 
     # ---- instrumented pass: per-kernel-class device time (events around every launch)
     prof = None
@@ -211,8 +228,12 @@ def run_native(args, rank, local_rank, world):
         _lib.check(m.lib.stb_profile_enable(m.ctx, 1))
         n_prof = min(args.steps, 10)
         for _ in range(n_prof):
-            step += 1
-            st._iterate(ea, eas, step, 0.02, 0.99, True)
+            if band is None:
+                one_iteration()
+            else:  # instrumented compute only (no collectives inside the event spans' critical path on rank 0)
+                step += 1
+                m.iterate_fwd(st.image)
+                m.iterate_bwd(st.image, grad, st._loss_host)
         torch.cuda.synchronize()
         ms = (ctypes.c_float * 10)()
         cnt = (ctypes.c_int * 10)()
@@ -243,14 +264,14 @@ def run_native(args, rank, local_rank, world):
     t_e2e = float(te.item())
     h2d = 2 * 3 * size * size * 4            # content + style fp32 tensors
     d2h = 32 * args.steps + 3 * size * size  # loss terms every step + final uint8 image
-    e2e = dict(value=world * args.steps / t_e2e, unit='it/s', h2d_bytes_per_step=h2d / args.steps,
+    e2e = dict(value=args.steps / t_e2e, unit='it/s', h2d_bytes_per_step=h2d / args.steps,
                d2h_bytes_per_step=d2h / args.steps,
                note='StyleTransfer.stylize(PIL inputs, single scale, K its, per-iteration loss callback) wall clock, '
                     'incl. PIL resize, target extraction, H2D/D2H')
 
     if rank == 0:
         peaks = measured_peaks()
-        conv_flops = CONV_FLOP_PER_PIXEL * size * size
+        conv_flops = CONV_FLOP_PER_PIXEL * h_loc * size  # this rank's rows (band + aprons when tiled)
         conv_ms = prof['conv_fwd']['ms_per_iter'] + prof['conv_bwd']['ms_per_iter']
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks['bf16_tflops_sustained']
@@ -262,17 +283,19 @@ def run_native(args, rank, local_rank, world):
                              'launches in an instrumented pass; traffic: see profiles/',
                         step_fraction=conv_ms / sum(v['ms_per_iter'] for v in prof.values()),
                         classes_ms_per_iter={k: round(v['ms_per_iter'], 4) for k, v in prof.items()},
-                        whole_step_tensor_frac=conv_flops * (1000.0 / ms_per_step) / 1e12 / peak)
+                        whole_step_tensor_frac=CONV_FLOP_PER_PIXEL * size * size * (1000.0 / ms_per_step) / 1e12 /
+                        (peak * world))
         cb = None
         if not args.no_cpu_baseline:
             cb = cpu_baseline(size)
         line = dict(metric='stylize iterations/sec at end_scale=2048', value=value, unit='it/s', n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
-                    scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic', impl='native',
+                    scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic', impl='native',
                     config=dict(workload=f'{size}x{size} single scale (BASELINE.json configs[2]), pooling=max, '
                                          'content+1 style, bf16 operands / fp32 accumulate, fp32 sqrtm+Adam',
-                                parallelism='single GPU' if world == 1 else f'{world} independent replicas '
-                                            '(spatial tiling not implemented yet)',
+                                parallelism='single GPU' if world == 1 else
+                                f'{world}-way spatial tiling: bands of {band.own_rows}+{band.top_apron + band.bottom_apron} '
+                                'halo rows (rank 0), 1 stats all-reduce + grad seam exchange + halo refresh per iteration',
                                 l2='working set per iteration (>= 2.4 GB of activations) far exceeds the 126 MB L2',
                                 final_loss=final_loss),
                     clocks=clocks, e2e=e2e, gpu_launches=int(round(launches * args.steps)), roofline=roofline,

@@ -89,6 +89,23 @@ STB_API int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_
                            float lr, float beta1, float beta2, float adam_eps, float ema_decay, int apply_update,
                            float* grad_out, float* loss_out_host8, void* stream);
 
+/* ------------------------------------------------------------------ spatial tiling across GPUs
+ * A context may work on a horizontal band (plus halo aprons) of a taller image: H passed to the other calls is the
+ * LOCAL height, rows [own_row0, own_row0+own_rows) (multiples of 16) are the band's own rows, H_global the full
+ * height.  Only own rows enter the statistics, losses and tap gradients.  Per iteration the host runs
+ *   stb_iterate_fwd  -> all-reduce(sum) of the stats block over the ranks (one NCCL call, ~2.4 MB)
+ *   stb_iterate_bwd  -> grad_out = d loss / d (local image) incl. contributions to the halo rows
+ *   [exchange + add the halo rows of grad_out with the neighbouring bands]
+ *   stb_adam_update  on the own rows, then refresh the halo rows of the image from the neighbours.
+ * With a band set, stb_style_stats returns RAW sums over the own rows (all-reduce, then divide by the global count). */
+STB_API int stb_set_band(stb_ctx* ctx, int enabled, int H_global, int own_row0, int own_rows);
+STB_API int stb_stats_block(stb_ctx* ctx, int H, int W, float** dev_ptr, size_t* n_floats);
+STB_API int stb_iterate_fwd(stb_ctx* ctx, const float* img, void* stream);
+STB_API int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_host8, void* stream);
+STB_API int stb_adam_update(float* img, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int H, int W,
+                            int row0, int rows, int64_t step, float lr, float beta1, float beta2, float adam_eps,
+                            float ema_decay, void* stream);
+
 /* ------------------------------------------------------------------ measurement (bench.py roofline leg)
  * CUDA-event timing per kernel class on the launching stream; classes in order: conv0_fwd_tv, conv_fwd, pool_fwd,
  * gram, sse, w2, conv_bwd, pool_bwd, conv0_bwd_adam, finalize (STB_PROF_CLASSES entries). */

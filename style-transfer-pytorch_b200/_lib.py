@@ -31,6 +31,11 @@ def _declare(lib):
         'stb_set_targets': [vp, i, i, vp, f, pp, pp, C.POINTER(f), f, f, vp],
         'stb_iterate': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, vp, vp],
         'stb_iterate_ex': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, i, vp, vp, vp],
+        'stb_set_band': [vp, i, i, i, i],
+        'stb_stats_block': [vp, i, i, pp, C.POINTER(sz)],
+        'stb_iterate_fwd': [vp, vp, vp],
+        'stb_iterate_bwd': [vp, vp, vp, vp, vp],
+        'stb_adam_update': [vp, vp, vp, vp, vp, i, i, i, i, i64, f, f, f, f, f, vp],
         'stb_profile_enable': [vp, i],
         'stb_profile_read': [vp, C.POINTER(f), C.POINTER(i), i],
         'stb_debug_activation': [vp, i, i, i, vp, sz, vp],
@@ -57,6 +62,7 @@ def _declare(lib):
 EXPORTS = [
     'stb_last_error', 'stb_ctx_create', 'stb_ctx_destroy', 'stb_workspace_bytes', 'stb_bind_workspace',
     'stb_style_stats', 'stb_content_features', 'stb_set_targets', 'stb_iterate', 'stb_iterate_ex',
+    'stb_set_band', 'stb_stats_block', 'stb_iterate_fwd', 'stb_iterate_bwd', 'stb_adam_update',
     'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation', 'stb_pack_weights', 'stb_test_pixel_gemm', 'stb_test_conv0_fwd', 'stb_test_conv0_bwd',
     'stb_test_pool', 'stb_test_gram', 'stb_test_gram_partials_floats', 'stb_test_w2', 'stb_test_w2_workspace_bytes',
 ]

@@ -32,6 +32,7 @@ struct Plan {
   size_t g_off[2];             // gradient ping-pong
   size_t gtv_off, tvp_off, ssep_off, gramp_off, stats_off, loss_off, ctarget_off;
   size_t stats_layer_off[5];   // in floats, inside the stats block: S_raw then sums per layer
+  size_t stats_scalars = 0, stats_floats = 0;
   size_t total = 0;
   int n_tv_partials = 0, n_sse_partials = 0;
 };
@@ -88,6 +89,11 @@ struct stb_ctx {
   float content_weight = 0.f, tv_weight = 0.f;
   float style_w[5] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // spatial tiling (multi-GPU): this context works on a horizontal band of a taller image.  The local image is the
+  // band plus halo aprons; only the "own" rows contribute to the statistics / losses / tap gradients.
+  int n_tv_partials = 0;
+  bool band_on = false;
+  int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
 };
 
 namespace {
@@ -122,6 +128,9 @@ void make_plan(const stb_ctx* ctx, int H, int W, Plan* pl) {
   pl->gramp_off = take(gp * 4);
   size_t sf = 0;
   for (int l = 0; l < 5; ++l) { pl->stats_layer_off[l] = sf; sf += (size_t)kStyleC[l] * kStyleC[l] + kStyleC[l]; }
+  pl->stats_scalars = sf;  // {content SSE, TV sum, 0, 0} ride at the tail so that one all-reduce covers everything
+  sf += 4;
+  pl->stats_floats = sf;
   pl->stats_off = take(sf * 4);
   pl->loss_off = take(64 * 4);
   pl->ctarget_off = take((size_t)pl->h[kContentConv] * pl->w[kContentConv] * 512 * 2);
@@ -147,12 +156,33 @@ int ensure_ws(const stb_ctx* ctx, const Plan& pl) {
 template <typename T>
 T* at(const stb_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->ws + off); }
 
+struct BandRows { int own0, rows, h_global; };
+// own rows of conv i's output grid (level = number of pools before it) and the global height at that level
+BandRows band_rows(const stb_ctx* ctx, const Plan& pl, int conv) {
+  int level = 0;
+  for (int i = 0; i < conv; ++i)
+    if (kPoolAfter[i]) ++level;
+  BandRows b;
+  if (!ctx->band_on) { b.own0 = 0; b.rows = pl.h[conv]; b.h_global = pl.h[conv]; return b; }
+  const bool is_bottom = ctx->band_own0 + ctx->band_own_rows >= pl.H;
+  b.own0 = ctx->band_own0 >> level;
+  b.rows = is_bottom ? pl.h[conv] - b.own0 : (ctx->band_own_rows >> level);
+  int hg = ctx->band_H_global;
+  for (int i = 0; i < level; ++i) hg /= 2;
+  b.h_global = hg;
+  return b;
+}
+
 // forward through conv `last_conv` (inclusive); do_tv also produces the TV gradient / loss partials
 int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool do_tv, cudaStream_t s) {
   int ntv = 0;
   ctx->prof.begin(PC_CONV0_FWD, s);
-  if (do_tv)
-    STB_TRY(launch_tv(img, pl.H, pl.W, ctx->tv_weight, at<float>(ctx, pl.gtv_off), at<float>(ctx, pl.tvp_off), &ntv, s));
+  if (do_tv) {
+    const BandRows br = band_rows(ctx, pl, 0);
+    STB_TRY(launch_tv(img, pl.H, pl.W, br.own0, br.rows, br.h_global, ctx->tv_weight, at<float>(ctx, pl.gtv_off),
+                      at<float>(ctx, pl.tvp_off), &ntv, s));
+  }
+  ctx->n_tv_partials = ntv;
   {  // conv0 on the tensor cores: im2col (hi/lo bf16 split, replicate pad, Normalize) + 1x1 pixel-GEMM + bias + ReLU
     bf16* col = at<bf16>(ctx, pl.g_off[0]);  // the gradient ping-pong buffer is idle during the forward pass
     STB_TRY(launch_im2col0(img, col, pl.H, pl.W, s));
@@ -190,11 +220,61 @@ int style_grams(stb_ctx* ctx, const Plan& pl, cudaStream_t s) {
     const int ci = kStyleConv[l];
     const int C = kStyleC[l];
     float* S = stats + pl.stats_layer_off[l];
-    STB_TRY(launch_gram(at<bf16>(ctx, pl.act_off[ci]), (long)pl.h[ci] * pl.w[ci], C, at<float>(ctx, pl.gramp_off), S,
-                        S + (size_t)C * C, s));
+    const BandRows br = band_rows(ctx, pl, ci);
+    STB_TRY(launch_gram(at<bf16>(ctx, pl.act_off[ci]) + (size_t)br.own0 * pl.w[ci] * C, (long)br.rows * pl.w[ci], C,
+                        at<float>(ctx, pl.gramp_off), S, S + (size_t)C * C, s));
   }
   ctx->prof.end(s);
   return STB_OK;
+}
+
+// deterministic single-block reduction of the content-SSE and TV partials into the stats tail
+__global__ void reduce2_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
+                               float* __restrict__ out) {
+  __shared__ float s_red[2][32];
+  float sa = 0.f, sb = 0.f;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) sa += a[i];
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sb += b[i];
+  sa = warp_sum(sa);
+  sb = warp_sum(sb);
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = sa; s_red[1][threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ta += s_red[0][i]; tb += s_red[1][i]; }
+    out[0] = ta; out[1] = tb; out[2] = 0.f; out[3] = 0.f;
+  }
+}
+
+__global__ void adam_rows_kernel(float* __restrict__ img, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                                 float* __restrict__ exp_avg_sq, float* __restrict__ ema, int H, int W, int row0,
+                                 int rows, AdamScalars ac) {
+  const long per = (long)rows * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * per; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / per);
+    const long r = i - (long)c * per;
+    const size_t idx = ((size_t)c * H + row0) * W + r;
+    const float g = grad[idx];
+    float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
+    m = m + (g - m) * ac.one_minus_b1;
+    v = v * ac.b2 + ac.one_minus_b2 * g * g;
+    const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
+    p = p - ac.step_size * (m / denom);
+    p = fminf(fmaxf(p, 0.f), 1.f);
+    e = e * ac.ema_decay + ac.one_minus_decay * p;
+    exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
+  }
+}
+
+AdamScalars make_adam_scalars(int64_t step, float lr, float beta1, float beta2, float adam_eps, float ema_decay) {
+  AdamScalars as{};
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  as.one_minus_b1 = 1.f - beta1; as.b2 = beta2; as.one_minus_b2 = 1.f - beta2;
+  as.step_size = (float)((double)lr / bc1);
+  as.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  as.eps = adam_eps; as.ema_decay = ema_decay; as.one_minus_decay = 1.f - ema_decay;
+  return as;
 }
 
 __global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long n, float scale) {
@@ -203,27 +283,12 @@ __global__ void scale_copy_kernel(const float* __restrict__ in, float* __restric
 }
 
 // loss = cw * sse / numel + sum_l style_l + tvw * tv   (python sum, left to right, ST:208/455)
-__global__ void finalize_loss_kernel(const float* __restrict__ sse_p, int n_sse, float content_scale,
-                                     const float* __restrict__ style_terms, const float* __restrict__ tv_p, int n_tv,
-                                     float tv_weight, float* __restrict__ out) {
-  __shared__ float s_red[32];
-  float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < n_sse; i += blockDim.x) a += sse_p[i];
-  for (int i = threadIdx.x; i < n_tv; i += blockDim.x) b += tv_p[i];
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
-  __syncthreads();
-  float ta = 0.f;
-  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) ta += s_red[i];
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = b;
-  __syncthreads();
+__global__ void finalize_loss_kernel(const float* __restrict__ scalars, float content_scale,
+                                     const float* __restrict__ style_terms, float tv_weight,
+                                     float* __restrict__ out) {
   if (threadIdx.x == 0) {
-    float tb = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tb += s_red[i];
-    const float content = ta * content_scale;
-    const float tv = tb * tv_weight;
+    const float content = scalars[0] * content_scale;
+    const float tv = scalars[1] * tv_weight;
     float loss = content;
     for (int l = 0; l < 5; ++l) loss += style_terms[l];
     loss += tv;
@@ -328,7 +393,8 @@ int stb_style_stats(stb_ctx* ctx, const float* img, int H, int W, float* const* 
   for (int l = 0; l < 5; ++l) {
     const int C = kStyleC[l];
     const int ci = kStyleConv[l];
-    const float inv = 1.f / ((float)pl.h[ci] * (float)pl.w[ci]);
+    // banded contexts return RAW sums over their own rows (the host all-reduces and normalises by the global count)
+    const float inv = ctx->band_on ? 1.f : 1.f / ((float)pl.h[ci] * (float)pl.w[ci]);
     const float* S = stats + pl.stats_layer_off[l];
     scale_copy_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(S, srm_out[l], (long)C * C, inv);
     scale_copy_kernel<<<1, 256, 0, s>>>(S + (size_t)C * C, mean_out[l], C, inv);
@@ -370,7 +436,7 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
     const int ci = kStyleConv[l];
     L.eps = eps;
     L.weight = style_w[l];
-    L.npix = (float)pl.h[ci] * (float)pl.w[ci];
+    L.npix = (float)band_rows(ctx, pl, ci).h_global * (float)pl.w[ci];
     L.S_raw = stats + pl.stats_layer_off[l];
     L.sums = L.S_raw + (size_t)C * C;
     STB_CUDA_CHECK(cudaMemcpyAsync(L.mean_t, mean_t[l], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
@@ -379,6 +445,8 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
   }
   STB_TRY(ctx->w2.upload_layers(s));
   STB_TRY(ctx->w2.build_targets(s));
+  if (ctx->band_on)  // TV gradient of the halo rows belongs to the neighbouring band: keep it zero here
+    STB_CUDA_CHECK(cudaMemsetAsync(at<float>(ctx, pl.gtv_off), 0, (size_t)3 * H * W * 4, s));
   ctx->content_weight = content_weight;
   ctx->tv_weight = tv_weight;
   ctx->tH = H; ctx->tW = W;
@@ -386,47 +454,53 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
   return STB_OK;
 }
 
-// One pass of ST:480-486.  apply_update = 0 evaluates loss / gradient only (test hook, L-BFGS closure).
-int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
-                   float beta1, float beta2, float adam_eps, float ema_decay, int apply_update, float* grad_out,
-                   float* loss_out_host8, void* stream) {
-  STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
-  STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate");
-  if (apply_update) STB_CHECK(exp_avg && exp_avg_sq && ema && step >= 1, STB_ERR_INVALID, "bad optimizer state");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int H = ctx->tH, W = ctx->tW;
-  Plan pl;
-  make_plan(ctx, H, W, &pl);
-  STB_TRY(ensure_ws(ctx, pl));
+}  // extern "C"
 
-  // ---- forward + statistics
+namespace {
+
+// phase 1: forward + this context's (band-local) statistics into the stats block
+int iterate_fwd(stb_ctx* ctx, const Plan& pl, const float* img, cudaStream_t s) {
   STB_TRY(forward(ctx, pl, img, NCONV - 1, true, s));
   STB_TRY(style_grams(ctx, pl, s));
-  const long n22 = (long)pl.h[kContentConv] * pl.w[kContentConv] * 512;
+  const BandRows b22 = band_rows(ctx, pl, kContentConv);
+  const size_t off22 = (size_t)b22.own0 * pl.w[kContentConv] * 512;
+  const long n22_local = (long)b22.rows * pl.w[kContentConv] * 512;
   int n_sse = 0;
   ctx->prof.begin(PC_SSE, s);
-  STB_TRY(launch_sse(at<bf16>(ctx, pl.act_off[kContentConv]), at<bf16>(ctx, pl.ctarget_off), n22,
+  STB_TRY(launch_sse(at<bf16>(ctx, pl.act_off[kContentConv]) + off22, at<bf16>(ctx, pl.ctarget_off) + off22, n22_local,
                      at<float>(ctx, pl.ssep_off), &n_sse, s));
+  reduce2_kernel<<<1, 1024, 0, s>>>(at<float>(ctx, pl.ssep_off), n_sse, at<float>(ctx, pl.tvp_off), ctx->n_tv_partials,
+                                    at<float>(ctx, pl.stats_off) + pl.stats_scalars);
   ctx->prof.end(s);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
+// phase 2: W2 losses on the (globally reduced) statistics, backward to the image, optional fused update
+int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
+                const AdamScalars& as, int apply_update, float* grad_out, float* loss_out_host8, cudaStream_t s) {
+  const int H = pl.H, W = pl.W;
+  const long n22 = (long)band_rows(ctx, pl, kContentConv).h_global * pl.w[kContentConv] * 512;  // global numel
   float* loss_dev = at<float>(ctx, pl.loss_off);
   ctx->prof.begin(PC_W2, s);
   STB_TRY(ctx->w2.forward_backward(loss_dev + 16, s));
   ctx->prof.end(s);
 
-  // ---- backward
   bf16* g[2] = {at<bf16>(ctx, pl.g_off[0]), at<bf16>(ctx, pl.g_off[1])};
   int cur = 0;
-  {  // tap 29: d loss / d conv12 pre-activation = mask * (F Gs / N + gmu / N)
+  {  // tap 29: d loss / d conv12 pre-activation = mask * (F Gs / N + gmu / N), own rows only
     const W2Layer& L = ctx->w2.host_layers[4];
+    const BandRows br = band_rows(ctx, pl, 12);
     PixelGemmArgs a;
     a.H = pl.h[12]; a.W = pl.w[12]; a.Cin = 0; a.Cout = 512; a.C2 = 512; a.mode = 1;
-    a.A2 = at<bf16>(ctx, pl.act_off[12]); a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
+    a.A2 = at<bf16>(ctx, pl.act_off[12]) + (size_t)br.own0 * pl.w[12] * 512;
+    a.a2_row0 = br.own0; a.a2_rows = br.rows; a.row_lo = br.own0; a.row_hi = br.own0 + br.rows;
+    a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
     a.mask_src = at<bf16>(ctx, pl.act_off[12]); a.out = g[cur];
     ctx->prof.begin(PC_CONV_BWD, s);
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
   }
-  int np = 3;
   for (int i = NCONV - 1; i >= 1; --i) {
     // g[cur] = gradient w.r.t. conv i pre-activation, [h_i][w_i][Cout_i]; produce gradient for conv i-1
     PixelGemmArgs a;
@@ -443,14 +517,18 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
                               pl.w[i - 1], kCout[i - 1], s));
       ctx->prof.end(s);
       cur ^= 1;
-      --np;
     } else {
       a.mode = 1;
       a.mask_src = at<bf16>(ctx, pl.act_off[i - 1]);
+      const BandRows br = band_rows(ctx, pl, i - 1);
+      a.row_lo = br.own0; a.row_hi = br.own0 + br.rows;
       for (int l = 0; l < 5; ++l)
         if (kStyleConv[l] == i - 1) {
           const W2Layer& L = ctx->w2.host_layers[l];
-          a.C2 = kStyleC[l]; a.A2 = at<bf16>(ctx, pl.act_off[i - 1]); a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
+          a.C2 = kStyleC[l];
+          a.A2 = at<bf16>(ctx, pl.act_off[i - 1]) + (size_t)br.own0 * pl.w[i - 1] * kStyleC[l];
+          a.a2_row0 = br.own0; a.a2_rows = br.rows;
+          a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
         }
       if (i - 1 == kContentConv) {
         a.ctarget = at<bf16>(ctx, pl.ctarget_off);
@@ -461,17 +539,6 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
       ctx->prof.end(s);
       cur ^= 1;
     }
-  }
-  (void)np;
-  // ---- conv0 dgrad + TV gradient + Adam + clamp + EMA
-  AdamScalars as{};
-  if (apply_update) {
-    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-    as.one_minus_b1 = 1.f - beta1; as.b2 = beta2; as.one_minus_b2 = 1.f - beta2;
-    as.step_size = (float)((double)lr / bc1);
-    as.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
-    as.eps = adam_eps; as.ema_decay = ema_decay; as.one_minus_decay = 1.f - ema_decay;
   }
   // conv0 dgrad of the interior on the tensor cores (output channels zero-padded 3 -> 64), borders + update in SIMT
   {
@@ -487,12 +554,95 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
                                 grad_out, H, W, as, apply_update, s));
   ctx->prof.end(s);
   ctx->prof.begin(PC_FINALIZE, s);
-  finalize_loss_kernel<<<1, 1024, 0, s>>>(at<float>(ctx, pl.ssep_off), n_sse, ctx->content_weight / (float)n22,
-                                          loss_dev + 16, at<float>(ctx, pl.tvp_off), pl.n_tv_partials,
-                                          ctx->tv_weight, loss_dev);
+  finalize_loss_kernel<<<1, 32, 0, s>>>(at<float>(ctx, pl.stats_off) + pl.stats_scalars,
+                                        ctx->content_weight / (float)n22, loss_dev + 16, ctx->tv_weight, loss_dev);
   ctx->prof.end(s);
   STB_CUDA_CHECK(cudaGetLastError());
-  if (loss_out_host8) STB_CUDA_CHECK(cudaMemcpyAsync(loss_out_host8, loss_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (loss_out_host8)
+    STB_CUDA_CHECK(cudaMemcpyAsync(loss_out_host8, loss_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return STB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// One pass of ST:480-486.  apply_update = 0 evaluates loss / gradient only (test hook, L-BFGS closure).
+int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
+                   float beta1, float beta2, float adam_eps, float ema_decay, int apply_update, float* grad_out,
+                   float* loss_out_host8, void* stream) {
+  STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
+  STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate");
+  STB_CHECK(!(ctx->band_on && apply_update), STB_ERR_STATE,
+            "banded contexts update through stb_iterate_fwd / all-reduce / stb_iterate_bwd / stb_adam_update");
+  if (apply_update) STB_CHECK(exp_avg && exp_avg_sq && ema && step >= 1, STB_ERR_INVALID, "bad optimizer state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan pl;
+  make_plan(ctx, ctx->tH, ctx->tW, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  STB_TRY(iterate_fwd(ctx, pl, img, s));
+  AdamScalars as{};
+  if (apply_update) as = make_adam_scalars(step, lr, beta1, beta2, adam_eps, ema_decay);
+  return iterate_bwd(ctx, pl, img, exp_avg, exp_avg_sq, ema, as, apply_update, grad_out, loss_out_host8, s);
+}
+
+// ---- spatial tiling across GPUs: the host drives
+//   stb_iterate_fwd -> all-reduce(stats block) -> stb_iterate_bwd -> seam exchange of grad -> stb_adam_update
+int stb_set_band(stb_ctx* ctx, int enabled, int H_global, int own_row0, int own_rows) {
+  STB_CHECK(ctx != nullptr, STB_ERR_INVALID, "null ctx");
+  if (enabled) {
+    STB_CHECK(H_global > 0 && own_row0 >= 0 && own_rows > 0 && own_row0 % 16 == 0, STB_ERR_INVALID,
+              "band rows must start on a multiple of 16 (four floor-mode pools), got own_row0=%d", own_row0);
+  }
+  ctx->band_on = enabled != 0;
+  ctx->band_H_global = H_global; ctx->band_own0 = own_row0; ctx->band_own_rows = own_rows;
+  ctx->targets_set = false;
+  return STB_OK;
+}
+
+int stb_stats_block(stb_ctx* ctx, int H, int W, float** dev_ptr, size_t* n_floats) {
+  STB_CHECK(ctx && dev_ptr && n_floats, STB_ERR_INVALID, "null argument");
+  Plan pl;
+  make_plan(ctx, H, W, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  *dev_ptr = at<float>(ctx, pl.stats_off);
+  *n_floats = pl.stats_floats;
+  return STB_OK;
+}
+
+int stb_iterate_fwd(stb_ctx* ctx, const float* img, void* stream) {
+  STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
+  STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate_fwd");
+  Plan pl;
+  make_plan(ctx, ctx->tH, ctx->tW, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  return iterate_fwd(ctx, pl, img, static_cast<cudaStream_t>(stream));
+}
+
+int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_host8, void* stream) {
+  STB_CHECK(ctx && img && grad_out, STB_ERR_INVALID, "null argument");
+  STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate_bwd");
+  Plan pl;
+  make_plan(ctx, ctx->tH, ctx->tW, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  AdamScalars as{};
+  return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, as, 0, grad_out, loss_out_host8,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// Adam + clamp + EMA on rows [row0, row0+rows) of [3][H][W] fp32 tensors (the band's own rows)
+int stb_adam_update(float* img, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int H, int W,
+                    int row0, int rows, int64_t step, float lr, float beta1, float beta2, float adam_eps,
+                    float ema_decay, void* stream) {
+  STB_CHECK(img && grad && exp_avg && exp_avg_sq && ema, STB_ERR_INVALID, "null argument");
+  STB_CHECK(row0 >= 0 && rows > 0 && row0 + rows <= H && step >= 1, STB_ERR_INVALID, "bad row range / step");
+  const AdamScalars as = make_adam_scalars(step, lr, beta1, beta2, adam_eps, ema_decay);
+  const long n = 3l * rows * W;
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grad, exp_avg, exp_avg_sq, ema, H,
+                                                                                  W, row0, rows, as);
+  STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
 

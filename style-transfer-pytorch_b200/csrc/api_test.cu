@@ -43,7 +43,7 @@ int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void*
                        float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream) {
   // product path of conv0: TV kernel, im2col (hi/lo split) and the 1x1 tcgen05 pixel-GEMM with bias + ReLU
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (gtv != nullptr) STB_TRY(launch_tv(img, H, W, tv_weight, gtv, tv_partials, n_partials, s));
+  if (gtv != nullptr) STB_TRY(launch_tv(img, H, W, 0, H, H, tv_weight, gtv, tv_partials, n_partials, s));
   bf16 *col = nullptr, *wp = nullptr;
   STB_CUDA_CHECK(cudaMalloc(&col, (size_t)H * W * 64 * 2));
   STB_CUDA_CHECK(cudaMalloc(&wp, 64 * 64 * 2));

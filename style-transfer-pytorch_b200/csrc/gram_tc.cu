@@ -14,16 +14,21 @@ namespace stb {
 
 namespace {
 
-constexpr int PK = 64;                 // pixels per pipeline stage
-constexpr int ATOM_BYTES = PK * 128;   // 64 channels x PK pixels, bf16
 constexpr int G_STAGES = 4;
 constexpr int G_THREADS = 64 + 128;
+constexpr int PK_MAX = 256;
 
+// PK = pixels per pipeline stage.  The narrow layers are pure HBM streams (C = 64: 8 KiB per 64 pixels), so they get
+// deep stages (32 KiB each, 128 KiB in flight per SM); C >= 256 needs the room for the separate A atoms.
 template <int BN>
 struct GCfg {
+  static constexpr int PK = BN == 64 ? 256 : (BN == 128 ? 128 : 64);
+  static constexpr int ATOM_BYTES = PK * 128;   // 64 channels x PK pixels, bf16
   static constexpr int B_ATOMS = BN / 64;
-  static constexpr int STAGE_BYTES = (B_ATOMS + 2) * ATOM_BYTES;
-  static constexpr int OFF_ONES = G_STAGES * STAGE_BYTES;
+  static constexpr int A_ATOMS = BN == 256 ? 2 : 0;  // C <= 128: the A block is always contained in the B block
+  static constexpr int STAGE_BYTES = (B_ATOMS + A_ATOMS) * ATOM_BYTES;
+  // + one atom of slack: with C = 64 the (ignored) upper 64 accumulator rows read one atom past the stage
+  static constexpr int OFF_ONES = G_STAGES * STAGE_BYTES + ATOM_BYTES;
   static constexpr int OFF_BAR = OFF_ONES + 2048;
   static constexpr int OFF_TMEMPTR = OFF_BAR + (2 * G_STAGES + 1) * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;
@@ -58,6 +63,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
   const bool contained = (i0 >= j0) && (i0 + m_valid <= j0 + BN);
   const long p_begin = (long)split * p.chunk_per_split;
   const long p_end = min(p.P, p_begin + p.chunk_per_split);
+  constexpr int PK = C::PK;
+  constexpr int ATOM_BYTES = C::ATOM_BYTES;
   const int n_k = (int)((p_end - p_begin + PK - 1) / PK);
 
   // constant ones tile (bf16 1.0 = 0x3F80)
@@ -78,7 +85,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (C::B_ATOMS + (contained ? 0 : 2)) * ATOM_BYTES;
+      const uint32_t tx_bytes = (C::B_ATOMS + (contained ? 0 : C::A_ATOMS)) * ATOM_BYTES;
       int s = 0;
       uint32_t ph = 0;
       for (int k = 0; k < n_k; ++k) {
@@ -88,7 +95,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
         const int pix = (int)(p_begin + (long)k * PK);
         for (int b = 0; b < C::B_ATOMS; ++b) tma_load_3d(st + b * ATOM_BYTES, &tmF, &full[s], j0 + b * 64, pix, 0);
         if (!contained)
-          for (int a = 0; a < 2; ++a)
+          for (int a = 0; a < C::A_ATOMS; ++a)
             tma_load_3d(st + (C::B_ATOMS + a) * ATOM_BYTES, &tmF, &full[s], i0 + a * 64, pix, 0);
         if (++s == G_STAGES) { s = 0; ph ^= 1; }
       }
@@ -155,13 +162,19 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-// sum partials in split order: out[i] = sum_s part[s][i]
+// sum partials in a fixed order (8 interleaved accumulators for memory-level parallelism, then a fixed tree):
+// out[i] = sum_s part[s][i]; deterministic run to run
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int n_splits) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < n_splits; ++k) s += part[(size_t)k * n + i];
-    out[i] = s;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= n_splits; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldg(part + (size_t)(k + u) * n + i);
+    }
+    for (; k < n_splits; ++k) a[0] += __ldg(part + (size_t)k * n + i);
+    out[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
 }
 
@@ -181,11 +194,14 @@ int launch_gram_cfg(const CUtensorMap& tm, const GParams& gp, int n_tiles, int n
 
 }  // namespace
 
+static int gram_pk(int BN) { return BN == 64 ? 256 : (BN == 128 ? 128 : 64); }
+
 int gram_num_splits(long P, int C) {
   const int BN = C >= 256 ? 256 : C;
+  const int PK = gram_pk(BN);
   const int n_tiles = ((C + 127) / 128) * (C / BN);
   long chunks = (P + PK - 1) / PK;
-  long want = (2L * num_sms() + n_tiles - 1) / n_tiles;  // ~2 CTAs' worth of splits per SM-slot
+  long want = (num_sms() + n_tiles - 1) / n_tiles;  // one CTA per SM
   if (want > chunks) want = chunks;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
@@ -203,6 +219,7 @@ int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, 
   const int n_tj = C / BN;
   const int n_ti = (C + 127) / 128;
   const int n_splits = gram_num_splits(P, C);
+  const int PK = gram_pk(BN);
   const long chunks = (P + PK - 1) / PK;
   const long per = (chunks + n_splits - 1) / n_splits;
   GParams gp;
@@ -211,6 +228,7 @@ int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, 
   gp.sum_partials = partials_ws + (size_t)n_splits * C * C;
   CUtensorMap tm;
   STB_TRY(make_tmap_bf16_3d(&tm, F, C, (uint64_t)P, 1, C * 2ull, (uint64_t)P * C * 2ull, 64, PK, 1));
+  static_assert(PK_MAX <= 256, "TMA box dimension limit");
   if (BN == 256) STB_TRY(launch_gram_cfg<256>(tm, gp, n_ti * n_tj, n_splits, stream));
   else if (BN == 128) STB_TRY(launch_gram_cfg<128>(tm, gp, n_ti * n_tj, n_splits, stream));
   else STB_TRY(launch_gram_cfg<64>(tm, gp, n_ti * n_tj, n_splits, stream));

@@ -54,10 +54,10 @@ __device__ float tv_gpad_slow(const float* __restrict__ x, int H, int W, int a, 
 // Nine-point L2 TV loss (ST:184-195) and its gradient (times tv_weight) on the raw image.  One thread per pixel,
 // all three channels; block partials of the loss are summed in fixed order by finalize_loss.
 __global__ void __launch_bounds__(256)
-tv_kernel(const float* __restrict__ img, int H, int W, TvConst tc, float* __restrict__ gtv,
+tv_kernel(const float* __restrict__ img, int H, int W, int row0, TvConst tc, float* __restrict__ gtv,
           float* __restrict__ tv_partials) {
   __shared__ float s_red[8];
-  const int y = blockIdx.y;
+  const int y = row0 + blockIdx.y;
   const int x = blockIdx.x * 256 + threadIdx.x;
   float tv_local = 0.f;
   if (x < W) {
@@ -106,33 +106,50 @@ tv_kernel(const float* __restrict__ img, int H, int W, TvConst tc, float* __rest
 // operand [H][W][64]: k < 27 the bf16 "hi" part of the 27 taps (k = (c*3+ky)*3+kx), 27 <= k < 54 the bf16 residual
 // ("lo", so the pair carries 16 mantissa bits), rest zero.  Step 2 is a 1x1 pixel-GEMM against [64][64] weights
 // laid out the same way, with conv0's bias and ReLU in its epilogue.
-// 8 lanes per pixel, lane `sub` produces the 16-byte chunk k = 8*sub .. 8*sub+7 (fully coalesced 128-byte rows).
+// One thread builds the 64 bf16 of its pixel in registers, the block's 256 rows are staged in smem and copied out
+// as fully coalesced 16-byte chunks (256 px x 128 B = 32 KiB contiguous).
 __global__ void __launch_bounds__(256)
 im2col0_kernel(const float* __restrict__ img, bf16* __restrict__ out, int H, int W) {
-  const long t = (long)blockIdx.x * 256 + threadIdx.x;
-  const long pix = t >> 3;
-  const int sub = (int)(t & 7);
-  if (pix >= (long)H * W) return;
-  const int y = (int)(pix / W), x = (int)(pix % W);
-  const float inv_std[3] = {(float)(1.0 / 0.229), (float)(1.0 / 0.224), (float)(1.0 / 0.225)};
-  float v8[8];
+  __shared__ __align__(16) uint32_t s_row[256 * 36];
+  const long total = (long)H * W;
+  const long base = (long)blockIdx.x * 256;
+  const long pix = base + threadIdx.x;
+  if (pix < total) {
+    const int y = (int)(pix / W), x = (int)(pix % W);
+    const float inv_std[3] = {(float)(1.0 / 0.229), (float)(1.0 / 0.224), (float)(1.0 / 0.225)};
+    const int ys[3] = {clampi(y - 1, 0, H - 1), y, clampi(y + 1, 0, H - 1)};
+    const int xs[3] = {clampi(x - 1, 0, W - 1), x, clampi(x + 1, 0, W - 1)};
+    float hi[28], lo[28];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = sub * 8 + e;
-    float val = 0.f;
-    if (k < 54) {
-      const int tap = k < 27 ? k : k - 27;
-      const int c = tap / 9, i = (tap % 9) / 3, j = tap % 3;
-      const float v = (__ldg(img + ((size_t)c * H + clampi(y + i - 1, 0, H - 1)) * W + clampi(x + j - 1, 0, W - 1)) -
-                       c_mean[c]) * inv_std[c];
-      const float h = __bfloat162float(__float2bfloat16(v));
-      val = k < 27 ? h : v - h;
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float v = (__ldg(img + ((size_t)c * H + ys[i]) * W + xs[j]) - c_mean[c]) * inv_std[c];
+          const float h = __bfloat162float(__float2bfloat16(v));
+          hi[(c * 3 + i) * 3 + j] = h;
+          lo[(c * 3 + i) * 3 + j] = v - h;
+        }
+    hi[27] = 0.f; lo[27] = 0.f;
+    uint32_t* row = s_row + threadIdx.x * 36;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {  // k layout: [hi0..hi26, lo0..lo26, 0 x 10]
+      const int k0 = 2 * q, k1 = 2 * q + 1;
+      const float a = k0 < 27 ? hi[k0] : (k0 < 54 ? lo[k0 - 27] : 0.f);
+      const float b = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : 0.f);
+      row[q] = pack_bf16x2(a, b);
     }
-    v8[e] = val;
   }
-  *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + sub * 8) =
-      make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
-                 pack_bf16x2(v8[6], v8[7]));
+  __syncthreads();
+  const long n_here = min((long)256, total - base);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)base * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int pl = idx >> 3, q = idx & 7;
+    if (pl < n_here) dst[idx] = *reinterpret_cast<const uint4*>(s_row + pl * 36 + q * 4);
+  }
 }
 
 __global__ void pack_w0_fwd_kernel(const float* __restrict__ w0, bf16* __restrict__ out) {
@@ -424,23 +441,25 @@ sse_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long n8, floa
 }  // namespace
 
 // ================================================================================================ launchers
-int launch_tv(const float* img, int H, int W, float tv_weight, float* gtv, float* tv_partials, int* n_partials,
-              cudaStream_t s) {
+int launch_tv(const float* img, int H, int W, int row0, int rows, int H_norm, float tv_weight, float* gtv,
+              float* tv_partials, int* n_partials, cudaStream_t s) {
+  // rows [row0, row0+rows) of the local H x W image are processed; H_norm is the height the loss means are taken over
+  // (the global image height when this image is a band of a taller one)
   TvConst tc{};
-  const double n1 = 3.0 * H * W, n3 = 3.0 * (H + 1.0) * (W + 1.0);
+  const double n1 = 3.0 * H_norm * W, n3 = 3.0 * (H_norm + 1.0) * (W + 1.0);
   tc.k1 = (float)(tv_weight * 4.0 / (3.0 * n1));
   tc.k3 = (float)(tv_weight * 4.0 / (12.0 * n3));
   tc.l1 = (float)(2.0 / (3.0 * n1));
   tc.l3 = (float)(2.0 / (12.0 * n3));
-  dim3 tgrid((W + 255) / 256, H);
+  dim3 tgrid((W + 255) / 256, rows);
   if (n_partials) *n_partials = tgrid.x * tgrid.y;
-  tv_kernel<<<tgrid, 256, 0, s>>>(img, H, W, tc, gtv, tv_partials);
+  tv_kernel<<<tgrid, 256, 0, s>>>(img, H, W, row0, tc, gtv, tv_partials);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
 
 int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s) {
-  const long threads = (long)H * W * 8;
+  const long threads = (long)H * W;
   im2col0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(img, out, H, W);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;

@@ -47,8 +47,8 @@ struct AdamScalars {  // torch/optim/adam.py:413-546 scalars, evaluated on the h
 };
 // TV loss partials + gradient (times tv_weight) on the raw image; im2col of the normalised replicate-padded image
 // for the tensor-core conv0 ([H][W][64] bf16: 27 hi taps, 27 lo residuals, 10 zeros) and the matching weights.
-int launch_tv(const float* img, int H, int W, float tv_weight, float* gtv, float* tv_partials, int* n_partials,
-              cudaStream_t s);
+int launch_tv(const float* img, int H, int W, int row0, int rows, int H_norm, float tv_weight, float* gtv,
+              float* tv_partials, int* n_partials, cudaStream_t s);
 int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s);
 int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s);
 // g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  gint (optional): zero-pad dgrad of g0

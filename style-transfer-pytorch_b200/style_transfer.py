@@ -20,6 +20,7 @@ from PIL import Image
 from torch.nn import functional as F
 
 from . import _lib
+from . import distributed as D
 
 CONV_CHANNELS = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 256), (256, 256),
                  (256, 512), (512, 512), (512, 512), (512, 512), (512, 512)]
@@ -85,6 +86,12 @@ class EMA:
         self.decay = float(decay)
         self.accum = self.decay
         self.value = input.detach() * (1 - self.decay)
+
+    @classmethod
+    def from_state(cls, value, accum, decay):
+        self = cls.__new__(cls)
+        self.decay, self.accum, self.value = float(decay), float(accum), value
+        return self
 
     def get(self):
         return self.value / (1 - self.accum)
@@ -170,6 +177,31 @@ class NativeVGG:
         _lib.check(self.lib.stb_content_features(self.ctx, _lib.ptr(image), h, w, _lib.ptr(out), _lib.cur_stream()))
         return out
 
+    # ------------------------------------------------------------------ spatial tiling (multi-GPU) plumbing
+    def set_band(self, enabled, h_global=0, own_row0=0, own_rows=0):
+        _lib.check(self.lib.stb_set_band(self.ctx, int(enabled), h_global, own_row0, own_rows))
+
+    def stats_view(self, h, w):
+        """fp32 tensor aliasing the stats block inside the workspace (what the ranks all-reduce)."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.stb_stats_block(self.ctx, h, w, ctypes.byref(p), ctypes.byref(n)))
+        off = p.value - self._ws.data_ptr()
+        return self._ws[off:off + 4 * n.value].view(torch.float32)
+
+    def iterate_fwd(self, image):
+        _lib.check(self.lib.stb_iterate_fwd(self.ctx, _lib.ptr(image), _lib.cur_stream()))
+
+    def iterate_bwd(self, image, grad, loss_host):
+        _lib.check(self.lib.stb_iterate_bwd(self.ctx, _lib.ptr(image), _lib.ptr(grad), _lib.ptr(loss_host),
+                                            _lib.cur_stream()))
+
+    def adam_update(self, image, grad, exp_avg, exp_avg_sq, ema, row0, rows, step, lr, avg_decay):
+        _, _, h, w = image.shape
+        _lib.check(self.lib.stb_adam_update(_lib.ptr(image), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                            _lib.ptr(ema), h, w, row0, rows, step, lr, 0.9, 0.99, 1e-8, avg_decay,
+                                            _lib.cur_stream()))
+
     def set_targets(self, h, w, content_target, content_weight, means, srms, layer_weights, tv_weight, eps=1e-4):
         mp, _k1 = _lib.ptr_array(means)
         sp, _k2 = _lib.ptr_array(srms)
@@ -179,7 +211,7 @@ class NativeVGG:
 
 
 class StyleTransfer:
-    def __init__(self, devices=['cpu'], pooling='max', *, vgg_weights=None):
+    def __init__(self, devices=['cpu'], pooling='max', *, vgg_weights=None, distributed=None):
         self.devices = [torch.device(device) for device in devices]
         self.image = None
         self.average = None
@@ -209,6 +241,13 @@ class StyleTransfer:
         self.model = NativeVGG(vgg_weights, pooling, dev)
         self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.last_loss_terms = None
+        # one process per GPU under torch.distributed: large scales are tiled spatially over the ranks
+        import torch.distributed as dist
+        self._dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if distributed is not None:
+            self._dist = bool(distributed) and self._dist
+        self._rank = dist.get_rank() if self._dist else 0
+        self._world = dist.get_world_size() if self._dist else 1
 
     # ------------------------------------------------------------------ results
     def get_image_tensor(self):
@@ -257,6 +296,18 @@ class StyleTransfer:
         _lib.check(m.lib.stb_iterate(m.ctx, _lib.ptr(self.image), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
                                      _lib.ptr(self.average.value), step, lr, 0.9, 0.99, 1e-8, avg_decay,
                                      _lib.ptr(self._loss_host) if want_loss else None, _lib.cur_stream()))
+        self.average.note_update()
+
+    def _iterate_banded(self, band, stats, grad, exp_avg, exp_avg_sq, step, lr, avg_decay):
+        """One iteration of a spatially tiled scale: this rank's band + the three exchanges (distributed.py)."""
+        m = self.model
+        m.iterate_fwd(self.image)
+        torch.distributed.all_reduce(stats)             # Gram sums, channel sums, content SSE, TV sum
+        m.iterate_bwd(self.image, grad, self._loss_host)
+        D.exchange_add_grad(grad, band)                 # seam reduce of the image gradient
+        m.adam_update(self.image, grad, exp_avg, exp_avg_sq, self.average.value, band.own0, band.own_rows, step, lr,
+                      avg_decay)
+        D.exchange_halo(self.image, band)               # refresh the halo rows of the iterate
         self.average.note_update()
 
     def loss_and_grad(self):
@@ -318,9 +369,17 @@ class StyleTransfer:
                     else:
                         sw, sh = size_to_fit(simg.size, style_size)
                     styles.append((sw, sh, _pil_to_tensor(simg.resize((sw, sh), Image.BICUBIC)).to(dev)))
-                self.model.ensure_workspace([(ch, cw)] + [(sh, sw) for sw, sh, _ in styles])
+                # multi-GPU: tile this scale into horizontal bands (None: too small, every rank runs the whole image)
+                band = D.make_band(ch, self._rank, self._world) if (self._dist and optimizer == 'adam') else None
+                h_loc = band.h_local if band is not None else ch
+                self.model.set_band(False)
+                self.model.ensure_workspace([(h_loc, cw)] + [(sh, sw) for sw, sh, _ in styles])
 
                 self.image = _resize(self.image.detach(), (ch, cw), 'bicubic').clamp_(0, 1).contiguous()
+                if band is not None:
+                    full_image = self.image
+                    self.image = D.local_slice(full_image, band)
+                    content = D.local_slice(content, band)
                 self.average = EMA(self.image, avg_decay)
 
                 print(f'Processing content image ({cw}x{ch})...')
@@ -337,7 +396,9 @@ class StyleTransfer:
                             acc.add_(m * weight)
                         for acc, s in zip(srms, s_i):
                             acc.add_(s * weight)
-                self.model.set_targets(ch, cw, content_target, per_content_weight, means, srms, self.style_weights,
+                if band is not None:
+                    self.model.set_band(True, ch, band.own0, band.own_rows)
+                self.model.set_targets(h_loc, cw, content_target, per_content_weight, means, srms, self.style_weights,
                                        tv_weight)
 
                 if optimizer == 'adam':
@@ -347,13 +408,21 @@ class StyleTransfer:
                     else:  # warm start at the new size, step counter carried over (ST:285-295, 460-462)
                         exp_avg = _resize(exp_avg, (ch, cw), 'bicubic').contiguous()
                         exp_avg_sq = _resize(exp_avg_sq, (ch, cw), 'bilinear').relu_().contiguous()
+                    if band is not None:
+                        if exp_avg.shape[2] != h_loc:
+                            exp_avg, exp_avg_sq = D.local_slice(exp_avg, band), D.local_slice(exp_avg_sq, band)
+                        stats = self.model.stats_view(h_loc, cw)
+                        grad = torch.empty_like(self.image)
                 else:
                     lbfgs = self._make_lbfgs()
                 torch.cuda.empty_cache()
 
                 actual_its = initial_iterations if scale == scales[0] else iterations
                 for i in range(1, actual_its + 1):
-                    if optimizer == 'adam':
+                    if optimizer == 'adam' and band is not None:
+                        step += 1
+                        self._iterate_banded(band, stats, grad, exp_avg, exp_avg_sq, step, step_size, avg_decay)
+                    elif optimizer == 'adam':
                         step += 1
                         self._iterate(exp_avg, exp_avg_sq, step, step_size, avg_decay, callback is not None)
                     else:
@@ -370,7 +439,13 @@ class StyleTransfer:
                         callback(STIterate(w=cw, h=ch, i=i, i_max=actual_its, loss=loss_value, time=time.time(),
                                            gpu_ram=gpu_ram))
 
-                self.image.copy_(self.average.get())
+                if band is not None:  # stitch the bands back together (identical full tensors on every rank)
+                    self.average = EMA.from_state(D.gather_rows(self.average.value, band), self.average.accum, avg_decay)
+                    exp_avg, exp_avg_sq = D.gather_rows(exp_avg, band), D.gather_rows(exp_avg_sq, band)
+                    self.image = self.average.get()
+                    self.model.set_band(False)
+                else:
+                    self.image.copy_(self.average.get())
 
         return self.get_image()
 

@@ -137,3 +137,16 @@ def test_full_size_properties(G, vgg_weights):
     # 256^2 loss of the same pair evaluated by the ORACLE (statistics of smooth fields are resolution independent
     # only loosely, so this is a sanity bound, not a parity claim)
     assert 0.0 < tr[0] < 10.0
+
+
+def test_two_gpu_banded_equals_single_gpu():
+    """Spatial tiling over 2 GPUs (NCCL): loss trace and result vs the single-GPU run (tools/dist_check.py)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', str(root / 'tools' / 'dist_check.py'),
+                        '384', '512', '5'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
