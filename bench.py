@@ -276,11 +276,16 @@ def run_native(args, rank, local_rank, world):
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks['bf16_tflops_sustained']
         launches = sum(v['launches_per_iter'] for v in prof.values())
+        traffic = None
+        tpath = ROOT / 'profiles' / 'r1_conv_traffic.json'
+        if tpath.exists() and size == 2048 and world == 1:
+            traffic = json.loads(tpath.read_text())['dram_total_bytes']  # dram read+write of the conv launches, ncu
         roofline = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-                        traffic=None, peak_source=f"{peaks['source']} (bf16_tflops_sustained)",
+                        traffic=traffic, peak_source=f"{peaks['source']} (bf16_tflops_sustained)",
                         kernel='pixel_gemm_kernel (tcgen05 conv fwd+dgrad, 25 launches/iter)',
                         note='algorithmic conv FLOPs/iter (1444608/pixel) / summed CUDA-event duration of the conv '
-                             'launches in an instrumented pass; traffic: see profiles/',
+                             'launches in an instrumented pass; traffic = DRAM bytes (read+write) of the same launches per '
+                             'iteration from one ncu --set full capture (profiles/r1_ncu_conv_summary.csv)',
                         step_fraction=conv_ms / sum(v['ms_per_iter'] for v in prof.values()),
                         classes_ms_per_iter={k: round(v['ms_per_iter'], 4) for k, v in prof.items()},
                         whole_step_tensor_frac=CONV_FLOP_PER_PIXEL * size * size * (1000.0 / ms_per_step) / 1e12 /
@@ -308,7 +313,7 @@ def run_native(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=2048)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])

@@ -144,67 +144,75 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // =============================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      const uint32_t a_base0 = smem_u32(smem + C::OFF_A);
-      const uint32_t b_base0 = smem_u32(smem + C::OFF_B);
-      int sa = 0, sb = 0, acc = 0;
-      uint32_t pa = 0, pb = 0, pacc = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&t_empty[acc], pacc ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (C::MT * BN);
-        uint32_t accum = 0;  // 0 only for the first weight stage of the tile (per-sub-tile accumulators)
-        for (int c = 0; c < n_chunks; ++c) {
-          for (int dx = 0; dx < 3; ++dx) {
-            mbar_wait(&a_full[sa], pa);
+    // =============================================================== MMA issuer
+    // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues the
+    // tcgen05.mma / commit instructions.  For N = 64 an MMA lasts only 32 cycles, so the issue path is kept short:
+    // loop-invariant descriptor high words, low words advanced by +2 per K step.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t a_hi = umma_desc_hi_sw128(C::A_PITCH);
+    constexpr uint32_t b_hi = umma_desc_hi_sw128(1024);
+    const uint32_t a_base0 = smem_u32(smem + C::OFF_A);
+    const uint32_t b_base0 = smem_u32(smem + C::OFF_B);
+    const bool leader = elect_one();
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&t_empty[acc], pacc ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (C::MT * BN);
+      uint32_t accum = 0;  // 0 only for the first weight stage of the tile (per-sub-tile accumulators)
+      for (int c = 0; c < n_chunks; ++c) {
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_stage = a_base0 + sa * C::A_STAGE_BYTES;
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint32_t a_stage = a_base0 + sa * C::A_STAGE_BYTES;
-            for (int dy = 0; dy < 3; ++dy) {
-              mbar_wait(&b_full[sb], pb);
-              tc_fence_after();
-              const uint32_t b_addr = b_base0 + sb * C::B_STAGE_BYTES;
+            if (leader) {
+              const uint32_t b_lo = umma_desc_lo(b_base0 + sb * C::B_STAGE_BYTES);
 #pragma unroll
               for (int m = 0; m < C::MT; ++m) {
-                const uint32_t a_addr = a_stage + dy * C::A_PITCH + m * 1024;
+                const uint32_t a_lo = umma_desc_lo(a_stage + dy * C::A_PITCH + m * 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(tmem_d + m * BN, umma_desc_sw128(a_addr + k * 32, 16, C::A_PITCH),
-                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum | (k > 0));
+                  umma_bf16_split(tmem_d + m * BN, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum | (k > 0));
               }
-              accum = 1;
               umma_commit(&b_empty[sb]);
-              if (++sb == C::NB) { sb = 0; pb ^= 1; }
+              if (dy == 2) umma_commit(&a_empty[sa]);
             }
-            umma_commit(&a_empty[sa]);
-            if (++sa == C::NA) { sa = 0; pa ^= 1; }
+            __syncwarp();
+            accum = 1;
+            if (++sb == C::NB) { sb = 0; pb ^= 1; }
           }
-        }
-        for (int c = 0; c < n_chunks2; ++c) {
-          mbar_wait(&a_full[sa], pa);
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t b_addr = b_base0 + sb * C::B_STAGE_BYTES;
-#pragma unroll
-          for (int m = 0; m < C::MT; ++m) {
-            const uint32_t a_addr = a_base0 + sa * C::A_STAGE_BYTES + m * 1024;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_d + m * BN, umma_desc_sw128(a_addr + k * 32, 16, C::A_PITCH),
-                        umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accum | (k > 0));
-          }
-          accum = 1;
-          umma_commit(&b_empty[sb]);
-          if (++sb == C::NB) { sb = 0; pb ^= 1; }
-          umma_commit(&a_empty[sa]);
           if (++sa == C::NA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&t_full[acc]);
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
+      for (int c = 0; c < n_chunks2; ++c) {
+        mbar_wait(&a_full[sa], pa);
+        mbar_wait(&b_full[sb], pb);
+        tc_fence_after();
+        if (leader) {
+          constexpr uint32_t a2_hi = umma_desc_hi_sw128(C::A_PITCH);
+          const uint32_t b_lo = umma_desc_lo(b_base0 + sb * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int m = 0; m < C::MT; ++m) {
+            const uint32_t a_lo = umma_desc_lo(a_base0 + sa * C::A_STAGE_BYTES + m * 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_split(tmem_d + m * BN, a_lo + 2 * k, a2_hi, b_lo + 2 * k, b_hi, idesc, accum | (k > 0));
+          }
+          umma_commit(&b_empty[sb]);
+          umma_commit(&a_empty[sa]);
+        }
+        __syncwarp();
+        accum = 1;
+        if (++sb == C::NB) { sb = 0; pb ^= 1; }
+        if (++sa == C::NA) { sa = 0; pa ^= 1; }
+      }
+      if (leader) umma_commit(&t_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    __syncwarp();
   } else {
     // =============================================================== epilogue (4 warps, TMEM lane group = warp % 4)
     const int wq = warp & 3;

@@ -66,9 +66,15 @@ def _resize(x, hw, mode):
         return F.interpolate(x, hw, mode=mode)
 
 
-def _pil_to_tensor(img):
-    arr = np.asarray(img.convert('RGB'), dtype=np.uint8)
-    return torch.from_numpy(arr.copy()).permute(2, 0, 1).to(torch.float32).div_(255).unsqueeze(0).contiguous()
+def _pil_to_tensor(img, device=None):
+    """TF.to_tensor semantics ([1,3,H,W] fp32 in [0,1], contiguous).  With a CUDA `device` the uint8 pixels are
+    uploaded (3 bytes/pixel instead of 12) and converted there."""
+    if img.mode != 'RGB':
+        img = img.convert('RGB')
+    t = torch.from_numpy(np.array(img, dtype=np.uint8))
+    if device is not None:
+        t = t.to(device, non_blocking=True)
+    return t.permute(2, 0, 1).to(torch.float32).div_(255).unsqueeze(0).contiguous()
 
 
 def load_vgg19_conv_weights():
@@ -145,6 +151,7 @@ class NativeVGG:
         if self._ws is not None and self._ws.numel() >= need + 1024:
             return False
         self._ws = None
+        torch.cuda.empty_cache()  # hand the old block back before asking for the bigger one
         self._ws = torch.empty(need + 2048, dtype=torch.uint8, device=self.device)
         base = self._ws.data_ptr()
         aligned = (base + 1023) // 1024 * 1024
@@ -259,7 +266,9 @@ class StyleTransfer:
         image = self.get_image_tensor()
         kind = image_type.lower()
         if kind == 'pil':
-            arr = image.mul(255).byte().permute(1, 2, 0).cpu().numpy()  # torchvision to_pil_image semantics
+            # torchvision to_pil_image semantics (mul(255).byte()); made HWC-contiguous on the device so that the
+            # host side is a single 3-byte/pixel copy
+            arr = image.mul(255).byte().permute(1, 2, 0).contiguous().cpu().numpy()
             return Image.fromarray(arr)
         if kind == 'np_uint16':
             return np.uint16(np.round(image.cpu().movedim(0, 2).numpy() * 65535))
@@ -357,18 +366,17 @@ class StyleTransfer:
         lbfgs = None
         with torch.cuda.device(dev), torch.no_grad():
             for scale in scales:
-                self.model.release_workspace()
                 torch.cuda.empty_cache()
 
                 cw, ch = size_to_fit(content_image.size, scale, scale_up=True)
-                content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC)).to(dev)
+                content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC), dev)
                 styles = []
                 for simg in style_images:
                     if style_size is None:
                         sw, sh = size_to_fit(simg.size, round(scale * style_scale_fac))
                     else:
                         sw, sh = size_to_fit(simg.size, style_size)
-                    styles.append((sw, sh, _pil_to_tensor(simg.resize((sw, sh), Image.BICUBIC)).to(dev)))
+                    styles.append((sw, sh, _pil_to_tensor(simg.resize((sw, sh), Image.BICUBIC), dev)))
                 # multi-GPU: tile this scale into horizontal bands (None: too small, every rank runs the whole image)
                 band = D.make_band(ch, self._rank, self._world) if (self._dist and optimizer == 'adam') else None
                 h_loc = band.h_local if band is not None else ch
