@@ -144,7 +144,7 @@ int stb_test_w2(const float* mean_t, const float* srm_t, const float* S_raw, con
   STB_TRY(eng.forward_backward(T.scal + 32, s));
   STB_CUDA_CHECK(cudaMemcpyAsync(loss_out, T.scal + W2S_LOSS, 4, cudaMemcpyDeviceToDevice, s));
   STB_CUDA_CHECK(cudaMemcpyAsync(gs_out, T.Gs, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
-  STB_CUDA_CHECK(cudaMemcpyAsync(csqrt_out, T.P, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+  STB_TRY(W2Engine::read_matrix(csqrt_out, T.P, C, s));
   // gmu_bias holds gmu / npix
   STB_CUDA_CHECK(cudaMemcpyAsync(gmu_out, T.gmu_bias, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
   return STB_OK;

@@ -102,31 +102,35 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_main = umma_idesc_bf16(128, BN, 1, 1);
-      constexpr uint32_t idesc_sum = umma_idesc_bf16(128, 16, 1, 1);
-      const uint32_t ones_addr = smem_u32(smem + C::OFF_ONES);
-      int s = 0;
-      uint32_t ph = 0, accum = 0;
-      for (int k = 0; k < n_k; ++k) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
+    // whole warp walks the k loop, one elected lane issues (short issue path: split descriptors, see conv_tc.cu)
+    constexpr uint32_t idesc_main = umma_idesc_bf16(128, BN, 1, 1);
+    constexpr uint32_t idesc_sum = umma_idesc_bf16(128, 16, 1, 1);
+    constexpr uint32_t hi_mn = umma_desc_hi_sw128(1024);  // MN-major: SBO = stride between 8-pixel groups
+    const uint32_t ones_lo = umma_desc_lo(smem_u32(smem + C::OFF_ONES), 1024);
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0, accum = 0;
+    for (int k = 0; k < n_k; ++k) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t b_addr = smem_u32(smem + s * C::STAGE_BYTES);
         const uint32_t a_addr = contained ? b_addr + ((i0 - j0) >> 6) * ATOM_BYTES : b_addr + C::B_ATOMS * ATOM_BYTES;
+        // MN-major SW128: LBO = stride between 64-channel atoms
+        const uint32_t a_lo = umma_desc_lo(a_addr, ATOM_BYTES), b_lo = umma_desc_lo(b_addr, ATOM_BYTES);
 #pragma unroll
         for (int ks = 0; ks < PK / 16; ++ks) {
-          // MN-major SW128: LBO = stride between 64-channel atoms, SBO = stride between 8-pixel groups
-          const uint64_t da = umma_desc_sw128(a_addr + ks * 2048, ATOM_BYTES, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + ks * 2048, ATOM_BYTES, 1024);
-          umma_bf16(tmem_base, da, db, idesc_main, accum);
-          if (tj == 0) umma_bf16(tmem_base + BN, da, umma_desc_sw128(ones_addr, 1024, 1024), idesc_sum, accum);
-          accum = 1;
+          umma_bf16_split(tmem_base, a_lo + ks * 128, hi_mn, b_lo + ks * 128, hi_mn, idesc_main, accum | (ks > 0));
+          if (tj == 0)
+            umma_bf16_split(tmem_base + BN, a_lo + ks * 128, hi_mn, ones_lo, hi_mn, idesc_sum, accum | (ks > 0));
         }
         umma_commit(&empty[s]);
-        if (++s == G_STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(t_full);
+      __syncwarp();
+      accum = 1;
+      if (++s == G_STAGES) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(t_full);
     __syncwarp();
   } else {
     const int wq = warp & 3;

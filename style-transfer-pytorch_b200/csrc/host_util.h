@@ -40,6 +40,10 @@ int set_error(int code, const char* fmt, ...);
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                       uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2);
 
+// 2-D fp32 row-major [rows][cols] tensor map, SWIZZLE_128B (box_cols * 4 bytes must be 128), zero OOB fill.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                     uint32_t box_rows);
+
 int num_sms();
 
 }  // namespace stb

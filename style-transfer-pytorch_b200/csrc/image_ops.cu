@@ -193,9 +193,25 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
       wr[t][c].y = s_w[((2 * lane + 1) * 3 + c) * 9 + t];
     }
 
-  for (long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5); wg < total; wg += nwarps) {
-    const int y = (int)(wg / strips);
-    const int xs = (int)(wg % strips) * 32;
+  // with gint the interior pixels are updated by adam_interior_kernel; only strips that contain border pixels are
+  // enumerated here: rows 0 and H-1 completely, first and last strip of every other row
+  const int side = strips >= 2 ? 2 : 1;
+  const long total_items = gint ? ((long)2 * strips + (long)(H > 2 ? H - 2 : 0) * side) : total;
+  for (long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5); wg < total_items; wg += nwarps) {
+    int y, xs;
+    if (!gint) {
+      y = (int)(wg / strips);
+      xs = (int)(wg % strips) * 32;
+    } else if (wg < strips) {
+      y = 0; xs = (int)wg * 32;
+    } else if (wg < 2l * strips) {
+      y = H - 1; xs = (int)(wg - strips) * 32;
+      if (H == 1) continue;
+    } else {
+      const long r = wg - 2l * strips;
+      y = 1 + (int)(r / side);
+      xs = (r % side == 0) ? 0 : (strips - 1) * 32;
+    }
     auto ld = [&](int yo, int xo) -> F2 {
       F2 r{0.f, 0.f};
       if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
@@ -268,16 +284,10 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
 
     const int x = xs + lane;
     if (x < W) {
-#pragma unroll
-      const bool from_tc = gint != nullptr && row_interior && x > 0 && x < W - 1;
-      float tcg[3] = {0.f, 0.f, 0.f};
-      if (from_tc) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(gint + ((size_t)y * W + x) * 64));
-        tcg[0] = bf16lo(u.x); tcg[1] = bf16hi(u.x); tcg[2] = bf16lo(u.y);
-      }
-      for (int c = 0; c < 3; ++c) {
+      const bool from_tc = gint != nullptr && row_interior && x > 0 && x < W - 1;  // done by adam_interior_kernel
+      for (int c = 0; c < 3 && !from_tc; ++c) {
         const size_t idx = ((size_t)c * H + y) * W + x;
-        const float g = (from_tc ? tcg[c] : keep[c]) / c_std[c] + (gtv ? gtv[idx] : 0.f);
+        const float g = keep[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
         if (grad_out) grad_out[idx] = g;
         if (apply_update) {
           float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
@@ -290,6 +300,35 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
           exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
         }
       }
+    }
+  }
+}
+
+// Interior pixels: the conv0 dgrad already sits in gint (bf16 NHWC, channels 0..2 valid) from the tensor cores; this
+// is the pure HBM-bound tail: Normalize backward + TV gradient + Adam + clamp + EMA, one thread per pixel.
+__global__ void __launch_bounds__(256)
+adam_interior_kernel(const bf16* __restrict__ gint, const float* __restrict__ gtv, float* __restrict__ img,
+                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ ema,
+                     float* __restrict__ grad_out, int H, int W, AdamScalars ac, int apply_update) {
+  const int y = blockIdx.y + 1;
+  const int x = blockIdx.x * 256 + threadIdx.x + 1;
+  if (y >= H - 1 || x >= W - 1) return;
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(gint + ((size_t)y * W + x) * 64));
+  const float tcg[3] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y)};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const size_t idx = ((size_t)c * H + y) * W + x;
+    const float g = tcg[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
+    if (grad_out) grad_out[idx] = g;
+    if (apply_update) {
+      float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
+      m = m + (g - m) * ac.one_minus_b1;
+      v = v * ac.b2 + ac.one_minus_b2 * g * g;
+      const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
+      p = p - ac.step_size * (m / denom);
+      p = fminf(fmaxf(p, 0.f), 1.f);
+      e = e * ac.ema_decay + ac.one_minus_decay * p;
+      exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
     }
   }
 }
@@ -474,7 +513,12 @@ int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s) {
 int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
                           const AdamScalars& a, int apply_update, cudaStream_t s) {
-  const long warps = (long)H * ((W + 31) / 32);
+  const int strips = (W + 31) / 32;
+  const long warps = gint ? (2l * strips + (long)(H > 2 ? H - 2 : 0) * (strips >= 2 ? 2 : 1)) : (long)H * strips;
+  if (gint && H > 2 && W > 2) {
+    dim3 grid((W - 2 + 255) / 256, H - 2);
+    adam_interior_kernel<<<grid, 256, 0, s>>>(gint, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a, apply_update);
+  }
   long want = (warps + 7) / 8;
   const long cap = (long)num_sms() * 2 * 4;  // persistent: a few waves of 8-warp CTAs
   const int blocks = (int)(want < cap ? want : cap);

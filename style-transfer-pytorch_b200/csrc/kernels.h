@@ -69,14 +69,16 @@ size_t gram_partials_floats(long P, int C);
 // F: [P][C] bf16 pixel-major.  S_raw [C][C] and sums [C] receive the un-normalised sums over the P pixels.
 int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
 
-// ---------------------------------------------------------------- W2 style loss engine, fp32 (w2.cu)
-struct GemmProb {  // D = alpha*op(A)*op(B) + alpha2*op(A2)*op(B2) + beta*Cadd + gamma*I, all n x n row-major fp32
-  const float *A, *B, *A2, *B2, *Cadd;
+// ---------------------------------------------------------------- W2 style loss engine (w2_tc.cu)
+// Every matrix of the chain is a (hi, lo) pair of fp32 planes, lo stored n*n floats after hi (3xTF32 split).
+struct TcProb {  // D = alpha * A * B^T(as stored) + gamma * I, all n x n row-major plane pairs
+  const CUtensorMap* amap;  // [hi, lo] tensor maps of A in the A role (128-row boxes), device memory
+  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B in the B role (64-row boxes)
   float* D;
-  float* red_out;  // optional: per-tile {sum of squares, trace} of D, [ (n/64)^2 ][2]
-  int n, transA, transB, transA2, transB2;
-  int sym;  // result is symmetric: compute tiles ti <= tj only and mirror them
-  float alpha, alpha2, beta, gamma;
+  float* red_out;  // optional: per-tile {sum of squares, trace} of D
+  int n;
+  float alpha, gamma;
+  int pad_;
 };
 enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };
 struct W2Layer {
@@ -85,10 +87,10 @@ struct W2Layer {
   float weight;     // style layer weight (ST:320-322)
   float npix;       // number of pixels the raw sums were taken over (global count under multi-GPU)
   float *S_raw, *sums;                 // inputs: reduced raw second moment [n][n] and channel sums [n]
-  float *mu, *cov;                     // current mean / covariance
-  float *mean_t, *srm_t, *cov_t, *P;   // target: mean, second raw moment, covariance, sqrtm(cov_t)
-  float *M, *X, *Y[2], *Z[2], *T;      // forward chain
-  float *A[2], *Q[2], *E, *X1, *X23, *U, *Gc, *Gs;  // backward chain
+  float *mu, *cov;                     // current mean / covariance (cov: plane pair)
+  float *mean_t, *srm_t, *cov_t, *P;   // target: mean, second raw moment, covariance (pair), sqrtm(cov_t) (pair)
+  float *M, *X, *Y[2], *Z[2], *T;      // forward chain (plane pairs)
+  float *A[2], *Q[2], *E, *X1, *X23, *U, *Gc, *Gs;  // backward chain (pairs; Gs, X1 single planes)
   float* gmu_bias;  // out: (d loss / d mean) / npix              -> per-channel bias of the tap-gradient GEMM
   bf16* gs_bf16;    // out: (G + G^T) / npix as bf16 [n][n]       -> B operand of the tap-gradient GEMM
   float* scal;      // W2S_* scalars
@@ -98,9 +100,10 @@ struct W2Round { int first_tile, n_tiles; };
 struct W2Engine {
   W2Layer host_layers[5];
   W2Layer* d_layers = nullptr;
-  GemmProb* d_probs = nullptr;
+  TcProb* d_probs = nullptr;
   uint32_t* d_tiles = nullptr;
-  std::vector<GemmProb> host_probs;
+  CUtensorMap* d_maps = nullptr;
+  std::vector<TcProb> host_probs;
   std::vector<W2Round> rounds;
   int r_target_begin = 0, r_target_end = 0, r_fwd_begin = 0, r_fwd_ns_begin = 0, r_fwd_end = 0, r_bwd_begin = 0,
       r_bwd_end = 0, gc_prob_first = 0;
@@ -111,6 +114,7 @@ struct W2Engine {
   int run_rounds(int r0, int r1, cudaStream_t s);
   int build_targets(cudaStream_t s);            // mean_t/srm_t -> cov_t, P = sqrtm_ns(cov_t)   (ST:152-160)
   int forward_backward(float* loss_terms, cudaStream_t s);  // S_raw/sums -> loss_terms[5], gs_bf16, gmu_bias
+  static int read_matrix(float* dst, const float* pair, int n, cudaStream_t s);  // dst = hi + lo (test hook)
 };
 
 }  // namespace stb

@@ -359,7 +359,12 @@ class StyleTransfer:
 
         scales = gen_scales(min_scale, end_scale)
         cw, ch = size_to_fit(content_image.size, scales[0], scale_up=True)
-        self.image = self._initial_image(init, content_image, style_images, style_weights, cw, ch).to(dev)
+        first_content = None
+        if init == 'content':  # the initial iterate IS the first scale's content tensor: convert/upload it once
+            first_content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC), dev)
+            self.image = first_content.clone()
+        else:
+            self.image = self._initial_image(init, content_image, style_images, style_weights, cw, ch).to(dev)
 
         exp_avg = exp_avg_sq = None
         step = 0
@@ -369,7 +374,10 @@ class StyleTransfer:
                 torch.cuda.empty_cache()
 
                 cw, ch = size_to_fit(content_image.size, scale, scale_up=True)
-                content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC), dev)
+                if scale == scales[0] and first_content is not None:
+                    content, first_content = first_content, None
+                else:
+                    content = _pil_to_tensor(content_image.resize((cw, ch), Image.BICUBIC), dev)
                 styles = []
                 for simg in style_images:
                     if style_size is None:
