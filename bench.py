@@ -197,6 +197,9 @@ def run_native(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    side = torch.cuda.Stream(device=dev)  # non-legacy stream: lets the library replay iterations as a CUDA graph
+    side.wait_stream(torch.cuda.current_stream(dev))
+    torch.cuda.set_stream(side)
     for _ in range(max(args.warmup, 3)):
         one_iteration()
     barrier()

@@ -5,6 +5,7 @@
 //   backward  ST:475       tap-gradient GEMMs folded into the dgrad chain, pool backward, conv0 dgrad
 //   update    ST:481-486   Adam + clamp + EMA fused into the last kernel
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -92,6 +93,19 @@ struct stb_ctx {
   // spatial tiling (multi-GPU): this context works on a horizontal band of a taller image.  The local image is the
   // band plus halo aprons; only the "own" rows contribute to the statistics / losses / tap gradients.
   int n_tv_partials = 0;
+  // device-resident optimiser scalars (so that an iteration is a fixed launch sequence -> CUDA graph)
+  AdamScalars* d_adam = nullptr;
+  long long* d_step = nullptr;
+  long long dev_step_mirror = -1;  // host's view of *d_step
+  // CUDA graph of one fused iteration, keyed by everything baked into the launches
+  struct GraphKey {
+    int H, W; const void *ws, *img, *m, *v, *ema, *loss; float lr, b1, b2, eps, decay;
+    bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+  };
+  GraphKey gkey{};
+  int gkey_hits = 0;
+  cudaGraphExec_t gexec = nullptr;
+  bool graphs_enabled = true;
   bool band_on = false;
   int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
 };
@@ -266,6 +280,22 @@ __global__ void adam_rows_kernel(float* __restrict__ img, const float* __restric
   }
 }
 
+// step counter and bias corrections live on the device: *step += 1, then the scalars of torch's single-tensor Adam
+// (torch/optim/adam.py:413-546) are evaluated in double exactly like the host path does
+__global__ void adam_scalars_kernel(long long* step, AdamScalars* out, float lr, float beta1, float beta2,
+                                    float adam_eps, float ema_decay) {
+  const long long t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)t);
+  AdamScalars as;
+  as.one_minus_b1 = 1.f - beta1; as.b2 = beta2; as.one_minus_b2 = 1.f - beta2;
+  as.step_size = (float)((double)lr / bc1);
+  as.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  as.eps = adam_eps; as.ema_decay = ema_decay; as.one_minus_decay = 1.f - ema_decay;
+  *out = as;
+}
+
 AdamScalars make_adam_scalars(int64_t step, float lr, float beta1, float beta2, float adam_eps, float ema_decay) {
   AdamScalars as{};
   const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
@@ -315,7 +345,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
   size_t bytes = 0;
   for (int i = 0; i < NCONV; ++i) {
     bytes += align_up((size_t)kCout[i] * 4, 256);
-    if (i == 0) bytes += align_up((size_t)64 * 27 * 4, 256) + align_up((size_t)9 * 64 * 64 * 2, 256) + 8192;
+    if (i == 0) bytes += align_up((size_t)64 * 27 * 4, 256) + align_up((size_t)9 * 64 * 64 * 2, 256) + 8192 + 512;
     else bytes += 2 * align_up((size_t)9 * kCout[i] * kCin[i] * 2, 256);
   }
   cudaError_t e = cudaMalloc(&ctx->owned, bytes);
@@ -339,6 +369,12 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
       STB_TRY(pack_weights_bwd(conv_w[i], ctx->wb[i], kCout[i], kCin[i], s));
     }
   }
+  ctx->d_adam = (AdamScalars*)take(256);
+  ctx->d_step = (long long*)take(256);
+  {
+    const char* e = getenv("STB_GRAPH");
+    ctx->graphs_enabled = !(e && e[0] == '0');
+  }
   ctx->w2_bytes = W2Engine::workspace_bytes();
   STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -352,6 +388,7 @@ void stb_ctx_destroy(stb_ctx* ctx) {
   if (ctx->owned) cudaFree(ctx->owned);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
   delete ctx;
 }
 
@@ -373,6 +410,8 @@ int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream) {
   STB_CUDA_CHECK(cudaStreamSynchronize(s));
   ctx->ws = static_cast<uint8_t*>(ptr);
   ctx->ws_bytes = bytes;
+  if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+  ctx->gkey = stb_ctx::GraphKey{};
   ctx->targets_set = false;
   STB_TRY(ctx->w2.init(ctx->ws, ctx->w2_bytes, kStyleC));
   ctx->w2_ready = true;
@@ -427,6 +466,8 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
   make_plan(ctx, H, W, &pl);
   STB_TRY(ensure_ws(ctx, pl));
   STB_CHECK(ctx->w2_ready, STB_ERR_STATE, "workspace not bound");
+  if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }  // weights are baked into the graph
+  ctx->gkey = stb_ctx::GraphKey{};
   const size_t cbytes = (size_t)pl.h[kContentConv] * pl.w[kContentConv] * 512 * 2;
   STB_CUDA_CHECK(cudaMemcpyAsync(at<bf16>(ctx, pl.ctarget_off), content_target_bf16, cbytes, cudaMemcpyDeviceToDevice, s));
   float* stats = at<float>(ctx, pl.stats_off);
@@ -478,7 +519,7 @@ int iterate_fwd(stb_ctx* ctx, const Plan& pl, const float* img, cudaStream_t s) 
 
 // phase 2: W2 losses on the (globally reduced) statistics, backward to the image, optional fused update
 int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
-                const AdamScalars& as, int apply_update, float* grad_out, float* loss_out_host8, cudaStream_t s) {
+                const AdamScalars* d_adam, int apply_update, float* grad_out, float* loss_out_host8, cudaStream_t s) {
   const int H = pl.H, W = pl.W;
   const long n22 = (long)band_rows(ctx, pl, kContentConv).h_global * pl.w[kContentConv] * 512;  // global numel
   float* loss_dev = at<float>(ctx, pl.loss_off);
@@ -551,7 +592,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
   }
   ctx->prof.begin(PC_CONV0_BWD_ADAM, s);
   STB_TRY(launch_conv0_bwd_adam(g[cur], g[cur ^ 1], ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
-                                grad_out, H, W, as, apply_update, s));
+                                grad_out, H, W, d_adam, apply_update, s));
   ctx->prof.end(s);
   ctx->prof.begin(PC_FINALIZE, s);
   finalize_loss_kernel<<<1, 32, 0, s>>>(at<float>(ctx, pl.stats_off) + pl.stats_scalars,
@@ -580,10 +621,58 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
   STB_TRY(ensure_ws(ctx, pl));
-  STB_TRY(iterate_fwd(ctx, pl, img, s));
-  AdamScalars as{};
-  if (apply_update) as = make_adam_scalars(step, lr, beta1, beta2, adam_eps, ema_decay);
-  return iterate_bwd(ctx, pl, img, exp_avg, exp_avg_sq, ema, as, apply_update, grad_out, loss_out_host8, s);
+  if (!apply_update) {
+    STB_TRY(iterate_fwd(ctx, pl, img, s));
+    return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad_out, loss_out_host8, s);
+  }
+  // the device step counter must read step-1 before this iteration (it is carried across scales like ST:461-462)
+  if (ctx->dev_step_mirror != step - 1) {
+    const long long v = step - 1;
+    STB_CUDA_CHECK(cudaMemcpyAsync(ctx->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaStreamSynchronize(s));  // `v` is a stack variable; this path runs once per scale at most
+  }
+  ctx->dev_step_mirror = step;
+  auto run = [&]() -> int {
+    STB_TRY(iterate_fwd(ctx, pl, img, s));
+    adam_scalars_kernel<<<1, 1, 0, s>>>(ctx->d_step, ctx->d_adam, lr, beta1, beta2, adam_eps, ema_decay);
+    return iterate_bwd(ctx, pl, img, exp_avg, exp_avg_sq, ema, ctx->d_adam, 1, grad_out, loss_out_host8, s);
+  };
+  // ---- CUDA graph: an iteration is ~110 launches with fixed arguments; replaying a captured graph removes the
+  // per-launch host cost and the tensor-map encodes (matters most at the small pyramid levels)
+  const bool legacy = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+  if (!ctx->graphs_enabled || ctx->prof.on || legacy || grad_out != nullptr) return run();
+  stb_ctx::GraphKey key{};
+  key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img; key.m = exp_avg; key.v = exp_avg_sq; key.ema = ema;
+  key.loss = loss_out_host8; key.lr = lr; key.b1 = beta1; key.b2 = beta2; key.eps = adam_eps; key.decay = ema_decay;
+  if (!(key == ctx->gkey)) {
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+    ctx->gkey = key;
+    ctx->gkey_hits = 0;
+  }
+  if (ctx->gexec) {
+    STB_CUDA_CHECK(cudaGraphLaunch(ctx->gexec, s));
+    return STB_OK;
+  }
+  if (++ctx->gkey_hits < 3) return run();  // eager first (lazy one-time setup must not happen inside a capture)
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->graphs_enabled = false;
+    return run();
+  }
+  const int rc = run();
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc != STB_OK || ce != cudaSuccess || graph == nullptr ||
+      cudaGraphInstantiate(&ctx->gexec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    ctx->gexec = nullptr;
+    ctx->graphs_enabled = false;  // fall back to eager launches for this context
+    return run();
+  }
+  cudaGraphDestroy(graph);
+  STB_CUDA_CHECK(cudaGraphLaunch(ctx->gexec, s));
+  return STB_OK;
 }
 
 // ---- spatial tiling across GPUs: the host drives
@@ -625,8 +714,7 @@ int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_h
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
   STB_TRY(ensure_ws(ctx, pl));
-  AdamScalars as{};
-  return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, as, 0, grad_out, loss_out_host8,
+  return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad_out, loss_out_host8,
                      static_cast<cudaStream_t>(stream));
 }
 

@@ -65,7 +65,6 @@ int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, f
                        void* stream) {
   // product path: interior via the tcgen05 dgrad (weights zero-padded 3 -> 64 channels), borders in SIMT
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AdamScalars as{};
   bf16 *gint = nullptr, *wp = nullptr;
   STB_CUDA_CHECK(cudaMalloc(&gint, (size_t)H * W * 64 * 2));
   STB_CUDA_CHECK(cudaMalloc(&wp, 9 * 64 * 64 * 2));
@@ -78,7 +77,7 @@ int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, f
   }
   if (rc == 0)
     rc = launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), gint, w0, gtv, nullptr, nullptr, nullptr, nullptr,
-                               grad_out, H, W, as, 0, s);
+                               grad_out, H, W, nullptr, 0, s);
   cudaStreamSynchronize(s);
   cudaFree(gint);
   cudaFree(wp);

@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint, const float* __restrict__ w0,
                       const float* __restrict__ gtv, float* __restrict__ img, float* __restrict__ exp_avg,
                       float* __restrict__ exp_avg_sq, float* __restrict__ ema, float* __restrict__ grad_out, int H,
-                      int W, AdamScalars ac, int apply_update) {
+                      int W, const AdamScalars* __restrict__ acp, int apply_update) {
   __shared__ float s_w[64 * 27];
+  AdamScalars ac{};
+  if (apply_update) ac = *acp;
   for (int i = threadIdx.x; i < 64 * 27; i += 256) s_w[i] = w0[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -309,7 +311,10 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
 __global__ void __launch_bounds__(256)
 adam_interior_kernel(const bf16* __restrict__ gint, const float* __restrict__ gtv, float* __restrict__ img,
                      float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ ema,
-                     float* __restrict__ grad_out, int H, int W, AdamScalars ac, int apply_update) {
+                     float* __restrict__ grad_out, int H, int W, const AdamScalars* __restrict__ acp,
+                     int apply_update) {
+  AdamScalars ac{};
+  if (apply_update) ac = *acp;  // written on the device by adam_scalars_kernel (CUDA-graph friendly)
   const int y = blockIdx.y + 1;
   const int x = blockIdx.x * 256 + threadIdx.x + 1;
   if (y >= H - 1 || x >= W - 1) return;
@@ -512,7 +517,7 @@ int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s) {
 
 int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
-                          const AdamScalars& a, int apply_update, cudaStream_t s) {
+                          const AdamScalars* a, int apply_update, cudaStream_t s) {
   const int strips = (W + 31) / 32;
   const long warps = gint ? (2l * strips + (long)(H > 2 ? H - 2 : 0) * (strips >= 2 ? 2 : 1)) : (long)H * strips;
   if (gint && H > 2 && W > 2) {

@@ -56,7 +56,7 @@ int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s);
 // taken from it, border pixels are evaluated here).  grad_out (optional) receives d loss/d image.
 int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
-                          const AdamScalars& a, int apply_update, cudaStream_t s);
+                          const AdamScalars* d_adam, int apply_update, cudaStream_t s);  // d_adam: DEVICE pointer
 // conv0 dgrad weights for the tensor-core path: fp32 OIHW [64][3][3][3] -> bf16 [9][64 (ci, 3 real)][64 (co)]
 int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s);
 int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s);
@@ -70,15 +70,15 @@ size_t gram_partials_floats(long P, int C);
 int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
 
 // ---------------------------------------------------------------- W2 style loss engine (w2_tc.cu)
-// Every matrix of the chain is a (hi, lo) pair of fp32 planes, lo stored n*n floats after hi (3xTF32 split).
-struct TcProb {  // D = alpha * A * B^T(as stored) + gamma * I, all n x n row-major plane pairs
+// Every matrix of the chain is 4 fp32 planes of n*n floats: hi, lo (3xTF32 split) and the same for its transpose.
+struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major plane pairs
   const CUtensorMap* amap;  // [hi, lo] tensor maps of A in the A role (128-row boxes), device memory
-  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B in the B role (64-row boxes)
+  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B in the B role (32 n x 32 k boxes, consumed MN-major)
   float* D;
   float* red_out;  // optional: per-tile {sum of squares, trace} of D
   int n;
   float alpha, gamma;
-  int pad_;
+  int write_t;  // also write the planes of D^T (needed when D is later a right factor)
 };
 enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };
 struct W2Layer {

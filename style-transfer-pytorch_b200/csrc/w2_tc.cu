@@ -12,10 +12,13 @@
 // GEMM only ever streams ready-made planes through TMA.
 //
 // All five layers advance in lock-step: one "round" = one grouped launch whose CTAs are 128 x 64 output tiles of
-// every layer's GEMM (75 or 150 CTAs).  Every B operand of the chain is a symmetric matrix (powers / polynomials of
-// symmetric matrices, P, cov) or is used transposed (U P^T), so both operands are plain row-major = K-major SW128
-// tiles and no transposed copy or MN-major descriptor is needed.  Tensor maps are encoded once per workspace
-// binding and read from device memory.
+// every layer's GEMM (75 or 150 CTAs).  Both tcgen05 operands are K-major SW128 tiles: A[m][k] comes from the
+// row-major planes of A, B[n][k] from the planes of B^T -- every matrix that is later used as a right factor is
+// therefore written TWICE by its producer (planes of D and of D^T; the transposed store is coalesced across the
+// warp because TMEM lane = row).  The product order of the coupled Newton-Schulz iteration (Y <- Y T, Z <- T Z) is
+// kept exactly: substituting a factor by its transpose -- harmless in exact arithmetic, everything being
+// symmetric -- turns the error recursion E' = E/2 into E' = E - A^(1/2) E A^(-1/2) / 2, which explodes for the
+// ill-conditioned covariances of real activations.  Tensor maps are encoded once per workspace binding.
 #include <map>
 #include <vector>
 
@@ -28,6 +31,10 @@ namespace {
 
 constexpr int TM = 128, TN = 64, TKF = 32;      // tile rows / cols, k floats per stage (128 B swizzle row)
 constexpr int T_STAGES = 4;
+constexpr int T_CHUNK = 4;                         // stages (128 k) per hi*hi accumulator
+constexpr int T_MAX_CHUNKS = 4;                    // n <= 512
+constexpr int T_TMEM_COLS = 512;                   // 4 x 64 hi*hi chunk accumulators + 64 for the cross terms
+constexpr int T_CROSS_COL = T_MAX_CHUNKS * TN;
 constexpr int A_PLANE_BYTES = TM * 128;          // 16 KiB
 constexpr int B_PLANE_BYTES = TN * 128;          // 8 KiB
 constexpr int T_STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 48 KiB
@@ -39,23 +46,33 @@ constexpr int T_THREADS = 64 + 128;
 constexpr int NRED = 64;   // max reduction partials per layer
 constexpr int NB = 32;     // helper-kernel CTAs per layer
 
+// x = hi + lo with both parts rounded to nearest TF32 (the tensor core would otherwise truncate them: a biased
+// error that the loss' cancellation amplifies); x - hi is exact in fp32.
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float v, float& h, float& l) {
+  h = rna_tf32(v);
+  l = rna_tf32(v - h);
+}
 __device__ __forceinline__ void store_split4(float* hi_ptr, float* lo_ptr, float4 v) {
   float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
   *reinterpret_cast<float4*>(hi_ptr) = h;
   *reinterpret_cast<float4*>(lo_ptr) = l;
 }
 __device__ __forceinline__ void store_split(float* m, size_t nn, size_t e, float v) {
-  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  float h, l;
+  split_tf32(v, h, l);
   m[e] = h;
-  m[nn + e] = v - h;
+  m[nn + e] = l;
 }
 __device__ __forceinline__ float load2(const float* m, size_t nn, size_t e) { return m[e] + m[nn + e]; }
 
-// D = alpha * A * B^T(as stored) + gamma * I on one 128 x 64 tile; A, B, D are (hi, lo) plane pairs.
+// D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 4 planes of n*n floats: hi, lo, hi^T, lo^T.
+// smem per stage: A planes [128 rows][32 k] and B^T planes [64 rows (n)][32 k], all K-major SW128.
 __global__ void __launch_bounds__(T_THREADS, 1)
 w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -78,7 +95,7 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
     mbar_init(t_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_ptr);
+  if (warp == 1) tmem_alloc<T_TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,19 +112,21 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
         uint8_t* st = smem + s * T_STAGE_BYTES;
         tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
         tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
-        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);
+        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
         tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
         if (++s == T_STAGES) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage
+    // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage.  The tensor core accumulates with
+    // truncation, so a long K chain drifts: hi*hi goes to a fresh TMEM accumulator every T_CHUNK stages and the
+    // small cross terms to their own; the epilogue adds them up in round-to-nearest fp32.
     constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
     constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
     const bool leader = elect_one();
     int s = 0;
-    uint32_t ph = 0, accum = 0;
+    uint32_t ph = 0;
     for (int k = 0; k < n_k; ++k) {
       mbar_wait(&full[s], ph);
       tc_fence_after();
@@ -118,14 +137,14 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
         const uint32_t b_l = umma_desc_lo(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
-          umma_tf32_split(tmem_base, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, accum | (kk > 0));
-          umma_tf32_split(tmem_base, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
-          umma_tf32_split(tmem_base, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, 1);
+          const uint32_t t_main = tmem_base + (k / T_CHUNK) * TN, t_cross = tmem_base + T_CROSS_COL;
+          umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, (k > 0) | (kk > 0));
+          umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
+          umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, (k % T_CHUNK > 0) | (kk > 0));
         }
         umma_commit(&empty[s]);
       }
       __syncwarp();
-      accum = 1;
       if (++s == T_STAGES) { s = 0; ph ^= 1; }
     }
     if (leader) umma_commit(t_full);
@@ -144,8 +163,24 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
-      tmem_ld_32x32(taddr + h * 32, v);
-      tmem_ld_wait();
+      {
+        float acc[32];
+        tmem_ld_32x32(taddr + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
+        const int n_chunks = (n_k + T_CHUNK - 1) / T_CHUNK;
+        for (int c = 1; c < n_chunks; ++c) {
+          tmem_ld_32x32(taddr + c * TN + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
+        }
+        tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(acc[e] + __uint_as_float(v[e]));
+      }
       if (valid) {
         const int gj0 = tj * TN + h * 32;
         float* dh = pr.D + (size_t)gi * n + gj0;
@@ -160,6 +195,11 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
             ssq = fmaf(o[e], o[e], ssq);
           }
           store_split4(dh + 4 * q, dl + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
+          if (pr.write_t) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 contiguous bytes
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              store_split(pr.D + 2 * nn, nn, (size_t)(gj0 + 4 * q + e) * n + gi, o[e]);
+          }
         }
       }
     }
@@ -178,7 +218,7 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tmem_base);
+  if (warp == 1) tmem_dealloc<T_TMEM_COLS>(tmem_base);
 }
 
 // ---- helpers: grid (5 layers, NB CTAs), 256 threads; reductions via fixed-order partials (deterministic)
@@ -215,6 +255,7 @@ __global__ void __launch_bounds__(256) w2_cov_kernel(const W2Layer* __restrict__
     float v = S[e] * inv_n - (sm[i] * inv_n) * (sm[j] * inv_n);
     if (i == j) v += L.eps;
     store_split(cov, nn, e, v);
+    store_split(cov + 2 * nn, nn, (size_t)j * n + i, v);
     ssq = fmaf(v, v, ssq);
   }
   ssq = block_sum_256(ssq, s_red);
@@ -250,9 +291,11 @@ __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restri
   const float norm = sqrtf(ss);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    store_split(L.Y[0], nn, e, load2(M, nn, e) / norm);
-    L.Z[0][e] = (i == j) ? 1.f : 0.f;
-    L.Z[0][nn + e] = 0.f;
+    const float y0 = load2(M, nn, e) / norm;
+    store_split(L.Y[0], nn, e, y0);
+    store_split(L.Y[0] + 2 * nn, nn, (size_t)j * n + i, y0);
+    const float z0 = (i == j) ? 1.f : 0.f;
+    L.Z[0][e] = z0; L.Z[0][nn + e] = 0.f; L.Z[0][2 * nn + e] = z0; L.Z[0][3 * nn + e] = 0.f;
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
 }
@@ -263,8 +306,12 @@ __global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   const float s = sqrtf(L.scal[W2S_NORM_A]);
-  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256)
-    store_split(L.P, nn, e, load2(L.Y[0], nn, e) * s);
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
+    const int i = e / n, j = e - i * n;
+    const float v = load2(L.Y[0], nn, e) * s;
+    store_split(L.P, nn, e, v);
+    store_split(L.P + 2 * nn, nn, (size_t)j * n + i, v);
+  }
 }
 
 // forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41).
@@ -282,8 +329,12 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   const float seed = -2.f * L.weight / (n * norm_r);    // grad_output / ||z|| with grad_output = -2 w / C * I
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    store_split(L.A[0], nn, e, load2(L.Y[0], nn, e) / norm_y);   // a = z / ||z||
-    store_split(L.Q[0], nn, e, (i == j) ? seed : 0.f);
+    const float a0 = load2(L.Y[0], nn, e) / norm_y;               // a = z / ||z||
+    store_split(L.A[0], nn, e, a0);
+    store_split(L.A[0] + 2 * nn, nn, (size_t)j * n + i, a0);
+    const float q0 = (i == j) ? seed : 0.f;
+    store_split(L.Q[0], nn, e, q0);
+    store_split(L.Q[0] + 2 * nn, nn, e, q0);
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) {
     const float cov_diff = (L.scal[W2S_TR_COV_T] + L.scal[W2S_TR_COV] - 2.f * tr_r) / n;
@@ -335,8 +386,8 @@ int W2Engine::read_matrix(float* dst, const float* pair, int n, cudaStream_t s) 
 
 // ================================================================================================ host engine
 size_t W2Engine::layer_floats(int n) {
-  // plane pairs: cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17 x 2); single: Gs, srm_t, X1 (3)
-  return (size_t)37 * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
+  // 4 planes (hi, lo, hi^T, lo^T): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
+  return (size_t)(17 * 4 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
 }
 
 size_t W2Engine::workspace_bytes() {
@@ -363,24 +414,29 @@ struct Builder {
     const size_t nn = (size_t)n * n;
     int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);       // A role, hi
     if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);  // A role, lo
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m, n, n, TKF, TN);       // B role, hi
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + nn, n, n, TKF, TN);  // B role, lo
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m + 2 * nn, n, n, TKF, TN);  // B role: rows of B^T, hi
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + 3 * nn, n, n, TKF, TN);  // B role, lo
     if (r) rc = r;
     map_index[m] = idx;
     return idx;
   }
-  void add(int n, float* D, const float* A, const float* B, float alpha, float gamma = 0.f, float* red_out = nullptr) {
+  // a_transposed: use A^T as the left factor (its planes sit 2*n*n floats after A's)
+  void add(int n, float* D, const float* A, const float* B, float alpha, float gamma = 0.f, float* red_out = nullptr,
+           int write_t = 1, int a_transposed = 0, int b_transposed = 0) {
     TcProb p{};
-    p.amap = d_maps + maps_for(A, n);
-    p.bmap = d_maps + maps_for(B, n) + 2;
-    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma;
+    const size_t nn = (size_t)n * n;
+    p.amap = d_maps + maps_for(a_transposed ? A + 2 * nn : A, n);
+    // B role reads rows of B^T = planes 2,3 of B; for B^T as right factor that is planes 0,1 of B, i.e. the
+    // "A-side" planes of B addressed through B-role boxes: register them under the key B - 2*nn
+    p.bmap = d_maps + maps_for(b_transposed ? B - 2 * nn : B, n) + 2;
+    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.write_t = write_t;
     const int idx = (int)probs.size();
     probs.push_back(p);
     for (int i = 0; i < (n + TM - 1) / TM; ++i)
       for (int j = 0; j < n / TN; ++j) tiles.push_back((uint32_t)idx << 16 | (uint32_t)i << 8 | (uint32_t)j);
   }
 };
-constexpr int MAX_MAPS = 5 * 20 * 4;
+constexpr int MAX_MAPS = 5 * 24 * 4;
 }  // namespace
 
 int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
@@ -391,7 +447,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int l = 0; l < 5; ++l) {
     W2Layer& L = host_layers[l];
     const int n = n_per_layer[l];
-    const size_t nn = (size_t)n * n * 4, pp = 2 * nn;  // single plane / (hi, lo) pair
+    const size_t nn = (size_t)n * n * 4, pp = 4 * nn;  // single plane / (hi, lo, hi^T, lo^T)
     L.n = n;
     L.eps = 1e-4f;
     L.cov = (float*)take(pp); L.M = (float*)take(pp); L.X = (float*)take(pp);
@@ -438,10 +494,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   // (b) iterate forward: X = P cov; M = X P; NS
   r_fwd_begin = (int)rounds.size();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }
   end_round();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red, 0); }
   end_round();
   r_fwd_ns_begin = (int)rounds.size();
   ns_rounds();
@@ -464,13 +520,13 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     }
     end_round();
   }
-  // after 12 its q is in Q[0].  U = P^T q = P q ; Gc = 0.5 U P^T + (w/C) I  (gamma patched per layer in upload_layers)
+  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I   (gamma patched per layer in upload_layers)
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0, 1, 0); }
   end_round();
   begin_round();
   gc_prob_first = (int)b.probs.size();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f, nullptr, 0, 0, 1); }
   end_round();
   r_bwd_end = (int)rounds.size();
   STB_CHECK(b.rc == 0, STB_ERR_CUDA, "W2 tensor map encoding failed: %s", last_error_string().c_str());

@@ -247,6 +247,8 @@ class StyleTransfer:
             vgg_weights = load_vgg19_conv_weights()
         self.model = NativeVGG(vgg_weights, pooling, dev)
         self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # iterations run on a dedicated (non-legacy) stream so that the library can replay them as a CUDA graph
+        self._stream = torch.cuda.Stream(device=dev)
         self.last_loss_terms = None
         # one process per GPU under torch.distributed: large scales are tiled spatially over the ranks
         import torch.distributed as dist
@@ -369,7 +371,8 @@ class StyleTransfer:
         exp_avg = exp_avg_sq = None
         step = 0
         lbfgs = None
-        with torch.cuda.device(dev), torch.no_grad():
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(self._stream), torch.no_grad():
             for scale in scales:
                 torch.cuda.empty_cache()
 
@@ -462,6 +465,7 @@ class StyleTransfer:
                     self.model.set_band(False)
                 else:
                     self.image.copy_(self.average.get())
+            self._stream.synchronize()
 
         return self.get_image()
 
