@@ -119,18 +119,38 @@ def cpu_port_iteration_time(size, iters, warm):
     return times[len(times) // 2], torch.get_num_threads()
 
 
+def cpu_reference_iteration_time(size, iters):
+    """Seconds per iteration of the UNMODIFIED reference's stylize() on the host cores (baseline/_ref install)."""
+    import torch
+    from oracle import reference_harness as RH
+    from oracle import st_oracle as O
+    wts = O.make_vgg_weights(1234)
+    content, style = O.synth_image(1, 16, size, size), O.synth_image(2, 32, size, size)
+    t, _ = RH.time_reference(size, iters, wts, content, style, devices=('cpu',))
+    return t, torch.get_num_threads()
+
+
 def cpu_baseline(size, budget_s=25.0):
     """Affine model t(px) = a + b*px from two bounded samples (the W2/sqrtm part, ~65 GFLOP, does not scale with
-    pixels; the conv part does), evaluated at size^2."""
-    t256, threads = cpu_port_iteration_time(256, 2, 1)
-    big = 512 if t256 * 4 * 3 < budget_s else 384
-    tbig, _ = cpu_port_iteration_time(big, 2, 1)
+    pixels; the conv part does), evaluated at size^2.  Times the unmodified reference (kind "reference") when its
+    install travelled with the repo (baseline/_ref), else the oracle port of the same loop body (kind "port")."""
+    from oracle import reference_harness as RH
+    if RH.reference_available():
+        kind, what = 'reference', 'unmodified reference StyleTransfer.stylize(devices=[cpu]), median of STIterate.time diffs'
+        t256, threads = cpu_reference_iteration_time(256, 3)
+        big = 512 if t256 * 4 * 6 < budget_s else 384
+        tbig, _ = cpu_reference_iteration_time(big, 3)
+    else:
+        kind, what = 'port', 'oracle port (torch-CPU explicit schedule), median of 2 its'
+        t256, threads = cpu_port_iteration_time(256, 2, 1)
+        big = 512 if t256 * 4 * 3 < budget_s else 384
+        tbig, _ = cpu_port_iteration_time(big, 2, 1)
     b = (tbig - t256) / (big * big - 256 * 256)
     a = max(t256 - b * 256 * 256, 0.0)
     t_full = a + b * size * size
-    return dict(value=1.0 / t_full, unit='it/s', cores=threads, kind='port',
-                sample=f'oracle port (torch-CPU explicit schedule): median of 2 its at 256^2 ({t256:.3f} s) and '
-                       f'{big}^2 ({tbig:.3f} s), affine-in-pixels extrapolation to {size}^2 ({t_full:.2f} s/it)')
+    return dict(value=1.0 / t_full, unit='it/s', cores=threads, kind=kind,
+                sample=f'{what}: 256^2 ({t256:.3f} s/it) and {big}^2 ({tbig:.3f} s/it), affine-in-pixels '
+                       f'extrapolation to {size}^2 ({t_full:.2f} s/it)')
 
 
 # ------------------------------------------------------------------------------------------------ arms
@@ -142,7 +162,7 @@ def run_reference(args, rank, world):
                 steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / cb['value'], higher_is_better=True,
                 scaling='strong', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'{args.size}x{args.size} single scale, pooling=max, content+1 style, '
-                                     'CPU reference path (oracle port of stylize() loop body)'),
+                                     'CPU reference path (' + cb['kind'] + ')'),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit='it/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -250,13 +270,16 @@ def run_native(args, rank, local_rank, world):
     e2e = None
     losses = []
     st2 = stb.StyleTransfer(devices=[str(dev)], pooling='max', vgg_weights=wts)
-    st2.stylize(content, [style], min_scale=size, end_scale=size, initial_iterations=2, callback=lambda it: None)
-    barrier()
     import contextlib
     import io
+    with contextlib.redirect_stdout(io.StringIO()):  # stylize() prints progress like the reference does
+        st2.stylize(content, [style], min_scale=size, end_scale=size, initial_iterations=2, callback=lambda it: None)
+    barrier()
+    # BASELINE.json's config runs 500 iterations at this scale; fewer would mostly time the per-call setup
+    e2e_its = max(args.steps, 500)
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
-        out = st2.stylize(content, [style], min_scale=size, end_scale=size, initial_iterations=args.steps,
+        out = st2.stylize(content, [style], min_scale=size, end_scale=size, initial_iterations=e2e_its,
                           callback=lambda it: losses.append(it.loss))
     _ = out.size
     torch.cuda.synchronize()
@@ -265,12 +288,13 @@ def run_native(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
-    h2d = 2 * 3 * size * size * 4            # content + style fp32 tensors
-    d2h = 32 * args.steps + 3 * size * size  # loss terms every step + final uint8 image
-    e2e = dict(value=args.steps / t_e2e, unit='it/s', h2d_bytes_per_step=h2d / args.steps,
-               d2h_bytes_per_step=d2h / args.steps,
-               note='StyleTransfer.stylize(PIL inputs, single scale, K its, per-iteration loss callback) wall clock, '
-                    'incl. PIL resize, target extraction, H2D/D2H')
+    h2d = 2 * 3 * size * size                # content + style uint8 pixels (converted to fp32 on the device)
+    d2h = 32 * e2e_its + 3 * size * size     # loss terms every step + final uint8 image
+    e2e = dict(value=e2e_its / t_e2e, unit='it/s', h2d_bytes_per_step=h2d / e2e_its,
+               d2h_bytes_per_step=d2h / e2e_its, iterations=e2e_its,
+               note='StyleTransfer.stylize(PIL inputs, single scale, per-iteration loss callback) wall clock over '
+                    f'{e2e_its} iterations (BASELINE.json config: 500 at this scale), incl. PIL resize, target '
+                    'extraction, H2D of the inputs, per-iteration loss D2H, final image D2H')
 
     if rank == 0:
         peaks = measured_peaks()

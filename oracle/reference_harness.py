@@ -1,9 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference (/root/reference) on CPU with the synthetic VGG fixture.
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference with the synthetic VGG fixture.
 
-Only usable in the build container (the GPU box has no /root/reference).  Used by tests/golden/make_golden.py to
-produce the committed golden vectors that pin oracle/st_oracle.py, and by tests that are skipped when the
-reference is absent.  The only thing patched is torchvision's checkpoint *download* (no network here): the
-reference code itself runs untouched.
+The reference tree is looked up at /root/reference (build container) and then at baseline/_ref (a git-ignored
+`pip install --no-deps --target baseline/_ref` of the same unmodified sources, which travels to the GPU box).  Used by
+tests/golden/make_golden.py to produce the committed golden vectors that pin oracle/st_oracle.py, by tests that are
+skipped when the reference is absent, and by bench.py's reference arm / cpu_baseline leg.  The only thing patched is
+torchvision's checkpoint *download* (no network here): the reference code itself runs untouched.
 """
 from __future__ import annotations
 
@@ -14,7 +15,8 @@ from pathlib import Path
 
 import torch
 
-REFERENCE_ROOT = Path('/root/reference')
+_CANDIDATES = [Path('/root/reference'), Path(__file__).resolve().parent.parent / 'baseline' / '_ref']
+REFERENCE_ROOT = next((c for c in _CANDIDATES if (c / 'style_transfer' / 'style_transfer.py').exists()), _CANDIDATES[0])
 
 
 def reference_available() -> bool:
@@ -68,8 +70,9 @@ def import_reference():
     return sys.modules[name + '.style_transfer']
 
 
-def run_reference(content_pil, style_pils, conv_weights, pooling='max', seed=0, quiet=True, **stylize_kwargs):
-    """Run reference StyleTransfer.stylize() on CPU; returns (final PIL-free image tensor, trace, st)."""
+def run_reference(content_pil, style_pils, conv_weights, pooling='max', seed=0, quiet=True, devices=('cpu',),
+                  **stylize_kwargs):
+    """Run reference StyleTransfer.stylize(); returns (final PIL-free image tensor, trace, st)."""
     ref = import_reference()
     trace = []
 
@@ -78,8 +81,18 @@ def run_reference(content_pil, style_pils, conv_weights, pooling='max', seed=0, 
 
     torch.manual_seed(seed)
     with patched_checkpoint(conv_weights):
-        st = ref.StyleTransfer(devices=['cpu'], pooling=pooling)
+        st = ref.StyleTransfer(devices=list(devices), pooling=pooling)
     out = io.StringIO()
     with contextlib.redirect_stdout(out if quiet else sys.stdout):
         st.stylize(content_pil, style_pils, callback=cb, **stylize_kwargs)
     return st.get_image_tensor(), trace, st
+
+
+def time_reference(size, iters, conv_weights, content_pil, style_pil, devices=('cpu',), skip=2):
+    """Seconds per iteration of the unmodified reference at size x size (single scale): median of the differences of
+    STIterate.time (ST:493), the first `skip` iterations excluded."""
+    _, trace, _ = run_reference(content_pil, [style_pil], conv_weights, devices=devices, min_scale=size,
+                                end_scale=size, initial_iterations=iters + skip + 1)
+    t = [r['time'] for r in trace]
+    d = sorted(b - a for a, b in zip(t[skip:-1], t[skip + 1:]))
+    return d[len(d) // 2], trace

@@ -70,15 +70,22 @@ size_t gram_partials_floats(long P, int C);
 int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
 
 // ---------------------------------------------------------------- W2 style loss engine (w2_tc.cu)
-// Every matrix of the chain is 4 fp32 planes of n*n floats: hi, lo (3xTF32 split) and the same for its transpose.
-struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major plane pairs
-  const CUtensorMap* amap;  // [hi, lo] tensor maps of A in the A role (128-row boxes), device memory
-  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B in the B role (32 n x 32 k boxes, consumed MN-major)
+// Every matrix of the chain is a (hi, lo) pair of fp32 planes, lo stored n*n floats after hi (3xTF32 split).
+struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major plane pairs, B symmetric
+  const CUtensorMap* amap;  // [hi, lo] tensor maps of A with 128-row boxes (device memory)
+  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B with 64-row boxes
+  const CUtensorMap* dmap;  // [hi, lo, hi, lo] tensor maps of D for the TMA stores: 128-row boxes, 64-row boxes
   float* D;
   float* red_out;  // optional: per-tile {sum of squares, trace} of D
   int n;
   float alpha, gamma;
-  int write_t;  // also write the planes of D^T (needed when D is later a right factor)
+  int sym;  // D is symmetric: only upper tiles are scheduled, every value is stored to (i,j) and (j,i)
+};
+constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152;
+struct W2Round {  // one grouped launch; travels as a __grid_constant__ kernel parameter (no dependent global loads)
+  int n_tiles, n_probs;
+  TcProb probs[W2_MAX_PROBS];
+  uint32_t tiles[W2_MAX_TILES];  // prob << 16 | tile row << 8 | tile col
 };
 enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };
 struct W2Layer {
@@ -96,17 +103,13 @@ struct W2Layer {
   float* scal;      // W2S_* scalars
   float* red;       // reduction partials {sum of squares, trace} x 64
 };
-struct W2Round { int first_tile, n_tiles; };
 struct W2Engine {
   W2Layer host_layers[5];
   W2Layer* d_layers = nullptr;
-  TcProb* d_probs = nullptr;
-  uint32_t* d_tiles = nullptr;
   CUtensorMap* d_maps = nullptr;
-  std::vector<TcProb> host_probs;
   std::vector<W2Round> rounds;
   int r_target_begin = 0, r_target_end = 0, r_fwd_begin = 0, r_fwd_ns_begin = 0, r_fwd_end = 0, r_bwd_begin = 0,
-      r_bwd_end = 0, gc_prob_first = 0;
+      r_bwd_end = 0, gc_round = 0;
   static size_t layer_floats(int n);
   static size_t workspace_bytes();
   int init(void* ws, size_t bytes, const int n_per_layer[5]);

@@ -12,13 +12,15 @@
 // GEMM only ever streams ready-made planes through TMA.
 //
 // All five layers advance in lock-step: one "round" = one grouped launch whose CTAs are 128 x 64 output tiles of
-// every layer's GEMM (75 or 150 CTAs).  Both tcgen05 operands are K-major SW128 tiles: A[m][k] comes from the
-// row-major planes of A, B[n][k] from the planes of B^T -- every matrix that is later used as a right factor is
-// therefore written TWICE by its producer (planes of D and of D^T; the transposed store is coalesced across the
-// warp because TMEM lane = row).  The product order of the coupled Newton-Schulz iteration (Y <- Y T, Z <- T Z) is
-// kept exactly: substituting a factor by its transpose -- harmless in exact arithmetic, everything being
-// symmetric -- turns the error recursion E' = E/2 into E' = E - A^(1/2) E A^(-1/2) / 2, which explodes for the
-// ill-conditioned covariances of real activations.  Tensor maps are encoded once per workspace binding.
+// every layer's GEMM (<= 98 CTAs, one wave).  Both tcgen05 operands are K-major SW128 tiles: A[m][k] from the
+// row-major planes of A and B[n][k] = B^T from the planes of B, which is only the same thing because every right
+// factor on this path is EXACTLY symmetric: cov, the Newton-Schulz iterates Y/Z/T, the Lyapunov iterates a/q/E and
+// P are all symmetric in exact arithmetic, and their producers enforce it bit-for-bit -- a symmetric result is
+// computed on the tiles that touch the upper triangle only (62 % of them at C=512) and each value is stored to
+// (i,j) and (j,i); the mirrored store is coalesced across the warp because TMEM lane = row.  Merely ASSUMING
+// symmetry (reading a non-mirrored product as its transpose) is not an option: it turns the error recursion of
+// the coupled iteration, E' = E/2, into E' = E - A^(1/2) E A^(-1/2) / 2, which explodes for the ill-conditioned
+// covariances of real activations (measured: NaN at 2048^2).  Tensor maps are encoded once per workspace binding.
 #include <map>
 #include <vector>
 
@@ -71,10 +73,25 @@ __device__ __forceinline__ void store_split(float* m, size_t nn, size_t e, float
 }
 __device__ __forceinline__ float load2(const float* m, size_t nn, size_t e) { return m[e] + m[nn + e]; }
 
-// D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 4 planes of n*n floats: hi, lo, hi^T, lo^T.
-// smem per stage: A planes [128 rows][32 k] and B^T planes [64 rows (n)][32 k], all K-major SW128.
-__global__ void __launch_bounds__(T_THREADS, 1)
-w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ tiles) {
+// D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 2 planes of n*n floats: hi, lo.
+// smem per stage: A planes [128 rows][32 k] and B planes [64 rows (n)][32 k] (B symmetric), all K-major SW128.
+//
+// Symmetric results and the 128 x 64 tiling.  With tile (ti, tj) covering rows [128 ti, +128) and columns [64 tj, +64):
+//   tj == 2 ti      ("A"): rows 0..63 are a self-mirroring 64 x 64 diagonal block, rows 64..127 lie below the diagonal
+//                          and are NOT stored (tile (ti, 2ti+1) mirrors into them);
+//   tj == 2 ti + 1  ("B"): rows 0..63 are strictly above the diagonal (stored + mirrored), rows 64..127 are a
+//                          self-mirroring diagonal block;
+//   tj >  2 ti + 1       : strictly above the diagonal: stored + mirrored;      tj < 2 ti: not scheduled.
+// Inside a diagonal block the value of (i,j), j < i, is taken from the accumulator of (j,i) through shared memory, so
+// the stored matrix is symmetric bit-for-bit.
+__host__ __device__ __forceinline__ bool tile_in_upper(int ti, int tj) { return tj >= 2 * ti; }
+static_assert(TM == 2 * TN, "tile classes above assume 128 x 64 tiles");
+
+constexpr int S_PITCH = TN + 1;                     // raw fp32 tile [128][65] in the (drained) stage-0 buffer
+constexpr int STG_OFF = T_STAGE_BYTES;              // 4 store tiles (2 column halves x hi/lo) of 16 KiB, SW128
+static_assert(TM * S_PITCH * 4 <= T_STAGE_BYTES && STG_OFF + 4 * A_PLANE_BYTES <= T_STAGES * T_STAGE_BYTES, "epilogue smem");
+
+__global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_constant__ W2Round rp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + T_OFF_BAR);
@@ -83,8 +100,8 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + T_OFF_TMEMPTR);
   float* s_red = reinterpret_cast<float*>(smem + T_OFF_RED);
 
-  const uint32_t t = tiles[blockIdx.x];
-  const TcProb pr = probs[t >> 16];
+  const uint32_t t = rp.tiles[blockIdx.x];
+  const TcProb& pr = rp.probs[t >> 16];
   const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
   const int n = pr.n;
   const int n_k = n / TKF;
@@ -94,6 +111,8 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
     for (int i = 0; i < T_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(t_full, 1);
     fence_barrier_init();
+    tma_prefetch_desc(pr.amap); tma_prefetch_desc(pr.amap + 1);
+    tma_prefetch_desc(pr.bmap); tma_prefetch_desc(pr.bmap + 1);
   }
   if (warp == 1) tmem_alloc<T_TMEM_COLS>(tmem_ptr);
   tc_fence_before();
@@ -112,10 +131,12 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
         uint8_t* st = smem + s * T_STAGE_BYTES;
         tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
         tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
-        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
+        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T = B
         tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
         if (++s == T_STAGES) { s = 0; ph ^= 1; }
       }
+      tma_prefetch_desc(pr.dmap); tma_prefetch_desc(pr.dmap + 1);
+      tma_prefetch_desc(pr.dmap + 2); tma_prefetch_desc(pr.dmap + 3);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -150,60 +171,97 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
     if (leader) umma_commit(t_full);
     __syncwarp();
   } else {
-    // ---- epilogue: alpha, +gamma I, hi/lo split, Frobenius / trace partials
+    // ---- epilogue (128 threads, TMEM lane = tile row)
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
     const int gi = ti * TM + r;
-    const bool valid = gi < n;
     const size_t nn = (size_t)n * n;
+    const int cls = pr.sym ? min(tj - 2 * ti, 2) : 3;       // 0: "A", 1: "B", 2: strictly upper, 3: not symmetric
+    const int mb = cls == 0 ? 0 : (cls == 1 ? TN : -1);     // first row of the self-mirroring block, if any
+    const int store_rows = cls == 0 ? TN : TM;
+    float* S = reinterpret_cast<float*>(smem);
+    uint8_t* stg = smem + STG_OFF;
     mbar_wait(t_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    float ssq = 0.f, tr = 0.f;
+    const int n_chunks = (n_k + T_CHUNK - 1) / T_CHUNK;
+    // pass 1: accumulators -> alpha, + gamma I -> raw tile in shared memory
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
-      {
-        float acc[32];
-        tmem_ld_32x32(taddr + h * 32, v);
+      float acc[32];
+      tmem_ld_32x32(taddr + h * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
+      for (int c = 1; c < n_chunks; ++c) {
+        tmem_ld_32x32(taddr + c * TN + h * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
-        const int n_chunks = (n_k + T_CHUNK - 1) / T_CHUNK;
-        for (int c = 1; c < n_chunks; ++c) {
-          tmem_ld_32x32(taddr + c * TN + h * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
-        }
-        tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(acc[e] + __uint_as_float(v[e]));
+        for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
       }
-      if (valid) {
-        const int gj0 = tj * TN + h * 32;
-        float* dh = pr.D + (size_t)gi * n + gj0;
-        float* dl = dh + nn;
+      tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
+      tmem_ld_wait();
+      const int gj0 = tj * TN + h * 32;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float o[4];
+      for (int e = 0; e < 32; ++e) {
+        float o = (acc[e] + __uint_as_float(v[e])) * pr.alpha;
+        if (gi == gj0 + e) o += pr.gamma;
+        S[r * S_PITCH + h * 32 + e] = o;
+      }
+    }
+    tc_fence_before();
+    named_bar_sync(1, 128);
+    // pass 2: symmetrise the diagonal block, split, stage for the TMA store, mirror
+    const bool in_block = mb >= 0 && r >= mb && r < mb + TN;
+    const int rl = r - mb;
+    const bool stored = r < store_rows && gi < n;
+    const bool mirrored = gi < n && (cls == 2 || (cls == 1 && r < TN));
+    float ssq = 0.f, tr = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
+      uint8_t* row_lo = row_hi + A_PLANE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = h * 32 + 4 * q + e;
+          o[e] = (in_block && c < rl) ? S[(mb + c) * S_PITCH + rl] : S[r * S_PITCH + c];
+          if (stored) {
+            ssq = fmaf(o[e], o[e], ssq);
+            if (gi == tj * TN + c) tr += o[e];
+          }
+        }
+        float vh[4], vl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(o[e], vh[e], vl[e]);
+        const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
+        *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+        *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+        if (mirrored) {  // (j,i) <- (i,j): for a fixed column the 32 lanes (consecutive rows) write 128 contiguous bytes
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            o[e] = __uint_as_float(v[4 * q + e]) * pr.alpha;
-            if (gi == gj0 + 4 * q + e) { o[e] += pr.gamma; tr += o[e]; }
+            const size_t at = (size_t)(tj * TN + h * 32 + 4 * q + e) * n + gi;
+            pr.D[at] = vh[e];
+            pr.D[nn + at] = vl[e];
             ssq = fmaf(o[e], o[e], ssq);
-          }
-          store_split4(dh + 4 * q, dl + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
-          if (pr.write_t) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 contiguous bytes
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              store_split(pr.D + 2 * nn, nn, (size_t)(gj0 + 4 * q + e) * n + gi, o[e]);
           }
         }
       }
     }
-    tc_fence_before();
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (r == 0) {
+      const CUtensorMap* dm = pr.dmap + (store_rows == TN ? 2 : 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+        tma_store_2d(dm + 1, stg + (h * 2 + 1) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+      }
+      tma_store_commit();
+    }
     if (pr.red_out != nullptr) {
       ssq = warp_sum(ssq);
       tr = warp_sum(tr);
@@ -215,6 +273,7 @@ w2_gemm_kernel(const TcProb* __restrict__ probs, const uint32_t* __restrict__ ti
         pr.red_out[(ti * ntj + tj) * 2 + 1] = (s_red[1] + s_red[3]) + (s_red[5] + s_red[7]);
       }
     }
+    if (r == 0) tma_store_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -236,7 +295,14 @@ __device__ __forceinline__ void sum_partials(const float* red, int count, float&
   a = 0.f; b = 0.f;
   for (int i = 0; i < count; ++i) { a += red[2 * i]; b += red[2 * i + 1]; }
 }
-__device__ __forceinline__ int gemm_tiles(int n) { return ((n + TM - 1) / TM) * (n / TN); }
+// partials of a symmetric GEMM result: only the tiles that touch the upper triangle were scheduled
+__device__ __forceinline__ void sum_partials_sym(const float* red, int n, float& a, float& b) {
+  a = 0.f; b = 0.f;
+  const int ntj = n / TN;
+  for (int ti = 0; ti < (n + TM - 1) / TM; ++ti)
+    for (int tj = 0; tj < ntj; ++tj)
+      if (tile_in_upper(ti, tj)) { a += red[(ti * ntj + tj) * 2]; b += red[(ti * ntj + tj) * 2 + 1]; }
+}
 
 // covariance from (reduced) raw sums:  mu = sums/N; cov = S_raw/N - mu mu^T + eps I     (ST:171-173, 177)
 // target mode: cov_t from (mean_t, srm_t), plus sum-of-squares partials of cov_t for the NS normalisation.
@@ -252,10 +318,10 @@ __global__ void __launch_bounds__(256) w2_cov_kernel(const W2Layer* __restrict__
   float ssq = 0.f;
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    float v = S[e] * inv_n - (sm[i] * inv_n) * (sm[j] * inv_n);
+    const int lo = min(i, j), hi = max(i, j);  // read the upper triangle of S: cov must be symmetric bit-for-bit
+    float v = S[(size_t)lo * n + hi] * inv_n - (sm[lo] * inv_n) * (sm[hi] * inv_n);
     if (i == j) v += L.eps;
     store_split(cov, nn, e, v);
-    store_split(cov + 2 * nn, nn, (size_t)j * n + i, v);
     ssq = fmaf(v, v, ssq);
   }
   ssq = block_sum_256(ssq, s_red);
@@ -287,15 +353,14 @@ __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restri
   const size_t nn = (size_t)n * n;
   const float* M = from_target ? L.cov_t : L.M;
   float ss, dummy;
-  sum_partials(L.red, from_target ? NB : gemm_tiles(n), ss, dummy);
+  if (from_target) sum_partials(L.red, NB, ss, dummy);
+  else sum_partials_sym(L.red, n, ss, dummy);
   const float norm = sqrtf(ss);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    const float y0 = load2(M, nn, e) / norm;
-    store_split(L.Y[0], nn, e, y0);
-    store_split(L.Y[0] + 2 * nn, nn, (size_t)j * n + i, y0);
-    const float z0 = (i == j) ? 1.f : 0.f;
-    L.Z[0][e] = z0; L.Z[0][nn + e] = 0.f; L.Z[0][2 * nn + e] = z0; L.Z[0][3 * nn + e] = 0.f;
+    store_split(L.Y[0], nn, e, load2(M, nn, e) / norm);
+    L.Z[0][e] = (i == j) ? 1.f : 0.f;
+    L.Z[0][nn + e] = 0.f;
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
 }
@@ -306,12 +371,8 @@ __global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   const float s = sqrtf(L.scal[W2S_NORM_A]);
-  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
-    const int i = e / n, j = e - i * n;
-    const float v = load2(L.Y[0], nn, e) * s;
-    store_split(L.P, nn, e, v);
-    store_split(L.P + 2 * nn, nn, (size_t)j * n + i, v);
-  }
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256)
+    store_split(L.P, nn, e, load2(L.Y[0], nn, e) * s);
 }
 
 // forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41).
@@ -321,7 +382,7 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   float ss, tr;
-  sum_partials(L.red, gemm_tiles(n), ss, tr);
+  sum_partials_sym(L.red, n, ss, tr);
   const float sq = sqrtf(L.scal[W2S_NORM_A]);
   const float norm_y = sqrtf(ss);
   const float norm_r = sq * norm_y;                     // ||R||_F
@@ -329,12 +390,8 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   const float seed = -2.f * L.weight / (n * norm_r);    // grad_output / ||z|| with grad_output = -2 w / C * I
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    const float a0 = load2(L.Y[0], nn, e) / norm_y;               // a = z / ||z||
-    store_split(L.A[0], nn, e, a0);
-    store_split(L.A[0] + 2 * nn, nn, (size_t)j * n + i, a0);
-    const float q0 = (i == j) ? seed : 0.f;
-    store_split(L.Q[0], nn, e, q0);
-    store_split(L.Q[0] + 2 * nn, nn, e, q0);
+    store_split(L.A[0], nn, e, load2(L.Y[0], nn, e) / norm_y);   // a = z / ||z||
+    store_split(L.Q[0], nn, e, (i == j) ? seed : 0.f);
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) {
     const float cov_diff = (L.scal[W2S_TR_COV_T] + L.scal[W2S_TR_COV] - 2.f * tr_r) / n;
@@ -386,8 +443,8 @@ int W2Engine::read_matrix(float* dst, const float* pair, int n, cudaStream_t s) 
 
 // ================================================================================================ host engine
 size_t W2Engine::layer_floats(int n) {
-  // 4 planes (hi, lo, hi^T, lo^T): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
-  return (size_t)(17 * 4 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
+  // plane pairs (hi, lo): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
+  return (size_t)(17 * 2 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
 }
 
 size_t W2Engine::workspace_bytes() {
@@ -400,8 +457,7 @@ size_t W2Engine::workspace_bytes() {
 
 namespace {
 struct Builder {
-  std::vector<TcProb> probs;
-  std::vector<uint32_t> tiles;
+  std::vector<W2Round>* rounds = nullptr;
   std::vector<CUtensorMap> maps;
   std::map<const float*, int> map_index;
   CUtensorMap* d_maps = nullptr;
@@ -412,28 +468,32 @@ struct Builder {
     const int idx = (int)maps.size();
     maps.resize(idx + 4);
     const size_t nn = (size_t)n * n;
-    int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);       // A role, hi
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);  // A role, lo
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m + 2 * nn, n, n, TKF, TN);  // B role: rows of B^T, hi
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + 3 * nn, n, n, TKF, TN);  // B role, lo
+    int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);           // 128-row boxes: A loads, D stores
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m, n, n, TKF, TN);       // 64-row boxes: B loads (B symmetric),
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + nn, n, n, TKF, TN);  // D stores of diagonal half tiles
     if (r) rc = r;
     map_index[m] = idx;
     return idx;
   }
-  // a_transposed: use A^T as the left factor (its planes sit 2*n*n floats after A's)
+  void begin_round() { rounds->emplace_back(); rounds->back().n_tiles = 0; rounds->back().n_probs = 0; }
+  // D = alpha A B + gamma I with B symmetric; sym: D is symmetric too (upper tiles + mirrored stores)
   void add(int n, float* D, const float* A, const float* B, float alpha, float gamma = 0.f, float* red_out = nullptr,
-           int write_t = 1, int a_transposed = 0, int b_transposed = 0) {
-    TcProb p{};
-    const size_t nn = (size_t)n * n;
-    p.amap = d_maps + maps_for(a_transposed ? A + 2 * nn : A, n);
-    // B role reads rows of B^T = planes 2,3 of B; for B^T as right factor that is planes 0,1 of B, i.e. the
-    // "A-side" planes of B addressed through B-role boxes: register them under the key B - 2*nn
-    p.bmap = d_maps + maps_for(b_transposed ? B - 2 * nn : B, n) + 2;
-    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.write_t = write_t;
-    const int idx = (int)probs.size();
-    probs.push_back(p);
+           int sym = 1) {
+    W2Round& R = rounds->back();
+    if (R.n_probs >= W2_MAX_PROBS) { rc = STB_ERR_STATE; return; }
+    TcProb& p = R.probs[R.n_probs];
+    p.amap = d_maps + maps_for(A, n);
+    p.bmap = d_maps + maps_for(B, n) + 2;
+    p.dmap = d_maps + maps_for(D, n);
+    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.sym = sym;
     for (int i = 0; i < (n + TM - 1) / TM; ++i)
-      for (int j = 0; j < n / TN; ++j) tiles.push_back((uint32_t)idx << 16 | (uint32_t)i << 8 | (uint32_t)j);
+      for (int j = 0; j < n / TN; ++j)
+        if (!sym || tile_in_upper(i, j)) {
+          if (R.n_tiles >= W2_MAX_TILES) { rc = STB_ERR_STATE; return; }
+          R.tiles[R.n_tiles++] = (uint32_t)R.n_probs << 16 | (uint32_t)i << 8 | (uint32_t)j;
+        }
+    ++R.n_probs;
   }
 };
 constexpr int MAX_MAPS = 5 * 24 * 4;
@@ -447,7 +507,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int l = 0; l < 5; ++l) {
     W2Layer& L = host_layers[l];
     const int n = n_per_layer[l];
-    const size_t nn = (size_t)n * n * 4, pp = 4 * nn;  // single plane / (hi, lo, hi^T, lo^T)
+    const size_t nn = (size_t)n * n * 4, pp = 2 * nn;  // single plane / (hi, lo) pair
     L.n = n;
     L.eps = 1e-4f;
     L.cov = (float*)take(pp); L.M = (float*)take(pp); L.X = (float*)take(pp);
@@ -469,9 +529,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   // ---- build the round lists once (pointers are stable)
   Builder b;
   b.d_maps = d_maps;
+  b.rounds = &rounds;
   rounds.clear();
-  auto begin_round = [&]() { rounds.push_back({(int)b.tiles.size(), 0}); };
-  auto end_round = [&]() { rounds.back().n_tiles = (int)b.tiles.size() - rounds.back().first_tile; };
+  auto begin_round = [&]() { b.begin_round(); };
+  auto end_round = [&]() {};
   auto ns_rounds = [&]() {  // 12 x { T = 1.5 I - 0.5 Z Y ; Y' = Y T, Z' = T Z }, result ends in Y[0]
     for (int it = 0; it < 12; ++it) {
       const int s = it & 1, d = s ^ 1;
@@ -494,10 +555,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   // (b) iterate forward: X = P cov; M = X P; NS
   r_fwd_begin = (int)rounds.size();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }  // not symmetric
   end_round();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red, 0); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red); }
   end_round();
   r_fwd_ns_begin = (int)rounds.size();
   ns_rounds();
@@ -520,34 +581,28 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     }
     end_round();
   }
-  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I   (gamma patched per layer in upload_layers)
+  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I with P^T = P bit-for-bit (gamma patched per
+  // layer in upload_layers).  U is not symmetric; Gc is, but its consumer forms Gc + Gc^T from all of it.
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0, 1, 0); }
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0); }
   end_round();
   begin_round();
-  gc_prob_first = (int)b.probs.size();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f, nullptr, 0, 0, 1); }
+  gc_round = (int)rounds.size() - 1;
+  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f, nullptr, 0); }
   end_round();
   r_bwd_end = (int)rounds.size();
-  STB_CHECK(b.rc == 0, STB_ERR_CUDA, "W2 tensor map encoding failed: %s", last_error_string().c_str());
+  STB_CHECK(b.rc == 0, STB_ERR_CUDA, "W2 round construction failed (%d): %s", b.rc, last_error_string().c_str());
   STB_CHECK((int)b.maps.size() <= MAX_MAPS, STB_ERR_WORKSPACE, "W2 tensor map table overflow (%zu)", b.maps.size());
 
-  host_probs = b.probs;
-  d_probs = (TcProb*)take(sizeof(TcProb) * b.probs.size());
-  d_tiles = (uint32_t*)take(sizeof(uint32_t) * b.tiles.size());
   STB_CHECK(off <= bytes, STB_ERR_WORKSPACE, "W2 workspace overflow (%zu > %zu)", off, bytes);
   STB_CUDA_CHECK(cudaMemcpy(d_maps, b.maps.data(), sizeof(CUtensorMap) * b.maps.size(), cudaMemcpyHostToDevice));
-  STB_CUDA_CHECK(cudaMemcpy(d_tiles, b.tiles.data(), sizeof(uint32_t) * b.tiles.size(), cudaMemcpyHostToDevice));
-  STB_CUDA_CHECK(cudaMemcpy(d_probs, b.probs.data(), sizeof(TcProb) * b.probs.size(), cudaMemcpyHostToDevice));
   STB_CUDA_CHECK(cudaMemcpy(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice));
   return STB_OK;
 }
 
 int W2Engine::upload_layers(cudaStream_t s) {
-  // layer weights enter the Gc round through gamma = w / C
-  for (int l = 0; l < 5; ++l) host_probs[gc_prob_first + l].gamma = host_layers[l].weight / host_layers[l].n;
-  STB_CUDA_CHECK(cudaMemcpyAsync(d_probs + gc_prob_first, host_probs.data() + gc_prob_first, sizeof(TcProb) * 5,
-                                 cudaMemcpyHostToDevice, s));
+  // layer weights enter the Gc round through gamma = w / C (rounds travel as kernel parameters)
+  for (int l = 0; l < 5; ++l) rounds[gc_round].probs[l].gamma = host_layers[l].weight / host_layers[l].n;
   STB_CUDA_CHECK(cudaMemcpyAsync(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice, s));
   return STB_OK;
 }
@@ -559,7 +614,7 @@ int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
     attr_set = true;
   }
   for (int r = r0; r < r1; ++r)
-    w2_gemm_kernel<<<rounds[r].n_tiles, T_THREADS, T_SMEM_BYTES, s>>>(d_probs, d_tiles + rounds[r].first_tile);
+    w2_gemm_kernel<<<rounds[r].n_tiles, T_THREADS, T_SMEM_BYTES, s>>>(rounds[r]);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
