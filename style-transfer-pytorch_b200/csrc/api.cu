@@ -197,14 +197,8 @@ int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool 
                       at<float>(ctx, pl.tvp_off), &ntv, s));
   }
   ctx->n_tv_partials = ntv;
-  {  // conv0 on the tensor cores: im2col (hi/lo bf16 split, replicate pad, Normalize) + 1x1 pixel-GEMM + bias + ReLU
-    bf16* col = at<bf16>(ctx, pl.g_off[0]);  // the gradient ping-pong buffer is idle during the forward pass
-    STB_TRY(launch_im2col0(img, col, pl.H, pl.W, s));
-    PixelGemmArgs a;
-    a.H = pl.H; a.W = pl.W; a.Cin = 0; a.Cout = 64; a.C2 = 64; a.mode = 0;
-    a.A2 = col; a.B2 = ctx->wf[0]; a.out = at<bf16>(ctx, pl.act_off[0]); a.bias = ctx->bias[0];
-    STB_TRY(launch_pixel_gemm(a, s));
-  }
+  // conv0 on the tensor cores: Normalize + replicate pad + hi/lo im2col rows built in smem, bias + ReLU epilogue
+  STB_TRY(launch_conv0_fwd(img, ctx->wf[0], ctx->bias[0], at<bf16>(ctx, pl.act_off[0]), pl.H, pl.W, s));
   ctx->prof.end(s);
   int np = 0;
   const bf16* cur = at<bf16>(ctx, pl.act_off[0]);

@@ -41,22 +41,14 @@ extern "C" {
 
 int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void* out_bf16, int H, int W,
                        float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream) {
-  // product path of conv0: TV kernel, im2col (hi/lo split) and the 1x1 tcgen05 pixel-GEMM with bias + ReLU
+  // product path of conv0: TV kernel and the fused im2col + tcgen05 GEMM + bias + ReLU kernel
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (gtv != nullptr) STB_TRY(launch_tv(img, H, W, 0, H, H, tv_weight, gtv, tv_partials, n_partials, s));
-  bf16 *col = nullptr, *wp = nullptr;
-  STB_CUDA_CHECK(cudaMalloc(&col, (size_t)H * W * 64 * 2));
+  bf16* wp = nullptr;
   STB_CUDA_CHECK(cudaMalloc(&wp, 64 * 64 * 2));
   int rc = pack_weights_conv0_fwd(w0, wp, s);
-  if (rc == 0) rc = launch_im2col0(img, col, H, W, s);
-  if (rc == 0) {
-    PixelGemmArgs a;
-    a.H = H; a.W = W; a.Cin = 0; a.Cout = 64; a.C2 = 64; a.mode = 0;
-    a.A2 = col; a.B2 = wp; a.out = static_cast<bf16*>(out_bf16); a.bias = b0;
-    rc = launch_pixel_gemm(a, s);
-  }
+  if (rc == 0) rc = launch_conv0_fwd(img, wp, b0, static_cast<bf16*>(out_bf16), H, W, s);
   cudaStreamSynchronize(s);
-  cudaFree(col);
   cudaFree(wp);
   return rc;
 }

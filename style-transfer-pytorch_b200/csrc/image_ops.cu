@@ -102,56 +102,8 @@ tv_kernel(const float* __restrict__ img, int H, int W, int row0, TvConst tc, flo
   }
 }
 
-// conv0 forward, tensor-core path, step 1: im2col of the normalised, replicate-padded image into a pixel-major bf16
-// operand [H][W][64]: k < 27 the bf16 "hi" part of the 27 taps (k = (c*3+ky)*3+kx), 27 <= k < 54 the bf16 residual
-// ("lo", so the pair carries 16 mantissa bits), rest zero.  Step 2 is a 1x1 pixel-GEMM against [64][64] weights
-// laid out the same way, with conv0's bias and ReLU in its epilogue.
-// One thread builds the 64 bf16 of its pixel in registers, the block's 256 rows are staged in smem and copied out
-// as fully coalesced 16-byte chunks (256 px x 128 B = 32 KiB contiguous).
-__global__ void __launch_bounds__(256)
-im2col0_kernel(const float* __restrict__ img, bf16* __restrict__ out, int H, int W) {
-  __shared__ __align__(16) uint32_t s_row[256 * 36];
-  const long total = (long)H * W;
-  const long base = (long)blockIdx.x * 256;
-  const long pix = base + threadIdx.x;
-  if (pix < total) {
-    const int y = (int)(pix / W), x = (int)(pix % W);
-    const float inv_std[3] = {(float)(1.0 / 0.229), (float)(1.0 / 0.224), (float)(1.0 / 0.225)};
-    const int ys[3] = {clampi(y - 1, 0, H - 1), y, clampi(y + 1, 0, H - 1)};
-    const int xs[3] = {clampi(x - 1, 0, W - 1), x, clampi(x + 1, 0, W - 1)};
-    float hi[28], lo[28];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float v = (__ldg(img + ((size_t)c * H + ys[i]) * W + xs[j]) - c_mean[c]) * inv_std[c];
-          const float h = __bfloat162float(__float2bfloat16(v));
-          hi[(c * 3 + i) * 3 + j] = h;
-          lo[(c * 3 + i) * 3 + j] = v - h;
-        }
-    hi[27] = 0.f; lo[27] = 0.f;
-    uint32_t* row = s_row + threadIdx.x * 36;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {  // k layout: [hi0..hi26, lo0..lo26, 0 x 10]
-      const int k0 = 2 * q, k1 = 2 * q + 1;
-      const float a = k0 < 27 ? hi[k0] : (k0 < 54 ? lo[k0 - 27] : 0.f);
-      const float b = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : 0.f);
-      row[q] = pack_bf16x2(a, b);
-    }
-  }
-  __syncthreads();
-  const long n_here = min((long)256, total - base);
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)base * 64);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = threadIdx.x + 256 * i;
-    const int pl = idx >> 3, q = idx & 7;
-    if (pl < n_here) dst[idx] = *reinterpret_cast<const uint4*>(s_row + pl * 36 + q * 4);
-  }
-}
-
+// conv0 forward weights in the split K layout of conv0_tc.cu: k < 27 the tap (c*3+ky)*3+kx (multiplies the bf16 "hi"
+// part of the pixel), 27 <= k < 54 the same tap again (multiplies the residual), rest zero.
 __global__ void pack_w0_fwd_kernel(const float* __restrict__ w0, bf16* __restrict__ out) {
   // out[n][k]: k < 27 -> w0[n][k]; 27 <= k < 54 -> w0[n][k-27]; else 0
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,13 +450,6 @@ int launch_tv(const float* img, int H, int W, int row0, int rows, int H_norm, fl
   dim3 tgrid((W + 255) / 256, rows);
   if (n_partials) *n_partials = tgrid.x * tgrid.y;
   tv_kernel<<<tgrid, 256, 0, s>>>(img, H, W, row0, tc, gtv, tv_partials);
-  STB_CUDA_CHECK(cudaGetLastError());
-  return STB_OK;
-}
-
-int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s) {
-  const long threads = (long)H * W;
-  im2col0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(img, out, H, W);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }

@@ -45,12 +45,14 @@ int pack_weights_bwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t 
 struct AdamScalars {  // torch/optim/adam.py:413-546 scalars, evaluated on the host in double like torch does
   float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps, ema_decay, one_minus_decay;
 };
-// TV loss partials + gradient (times tv_weight) on the raw image; im2col of the normalised replicate-padded image
-// for the tensor-core conv0 ([H][W][64] bf16: 27 hi taps, 27 lo residuals, 10 zeros) and the matching weights.
+// TV loss partials + gradient (times tv_weight) on the raw image; weights of the tensor-core conv0 in its split
+// K layout (27 hi taps, 27 lo residuals, 10 zeros).
 int launch_tv(const float* img, int H, int W, int row0, int rows, int H_norm, float tv_weight, float* gtv,
               float* tv_partials, int* n_partials, cudaStream_t s);
-int launch_im2col0(const float* img, bf16* out, int H, int W, cudaStream_t s);
 int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s);
+// conv0 forward on tcgen05 with the im2col rows built in shared memory (conv0_tc.cu); out: bf16 NHWC [H][W][64]
+int launch_conv0_fwd(const float* img, const bf16* w0_packed, const float* bias, bf16* out, int H, int W,
+                     cudaStream_t s);
 // g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  gint (optional): zero-pad dgrad of g0
 // through conv0 computed on the tensor cores, bf16 NHWC [H][W][64] with channels 0..2 valid (interior pixels are
 // taken from it, border pixels are evaluated here).  grad_out (optional) receives d loss/d image.
