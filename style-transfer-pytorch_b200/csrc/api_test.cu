@@ -55,23 +55,21 @@ int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void*
 
 int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
                        void* stream) {
-  // product path: interior via the tcgen05 dgrad (weights zero-padded 3 -> 64 channels), borders in SIMT
+  // product path: interior via the tcgen05 dgrad (N = 16) with the image-space epilogue, borders in SIMT
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  bf16 *gint = nullptr, *wp = nullptr;
-  STB_CUDA_CHECK(cudaMalloc(&gint, (size_t)H * W * 64 * 2));
+  bf16* wp = nullptr;
   STB_CUDA_CHECK(cudaMalloc(&wp, 9 * 64 * 64 * 2));
   int rc = pack_weights_conv0_bwd(w0, wp, s);
   if (rc == 0) {
     PixelGemmArgs a;
-    a.H = H; a.W = W; a.Cin = 64; a.Cout = 64; a.mode = 2;
-    a.A = static_cast<const bf16*>(g0_bf16); a.Bw = wp; a.out = gint;
+    a.H = H; a.W = W; a.Cin = 64; a.Cout = 16; a.mode = 3;
+    a.A = static_cast<const bf16*>(g0_bf16); a.Bw = wp; a.gtv = gtv; a.grad_out = grad_out;
     rc = launch_pixel_gemm(a, s);
   }
   if (rc == 0)
-    rc = launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), gint, w0, gtv, nullptr, nullptr, nullptr, nullptr,
+    rc = launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), true, w0, gtv, nullptr, nullptr, nullptr, nullptr,
                                grad_out, H, W, nullptr, 0, s);
   cudaStreamSynchronize(s);
-  cudaFree(gint);
   cudaFree(wp);
   return rc;
 }

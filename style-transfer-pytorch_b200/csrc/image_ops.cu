@@ -122,7 +122,7 @@ __global__ void pack_w0_fwd_kernel(const float* __restrict__ w0, bf16* __restric
 struct F2 { float x, y; };
 
 __global__ void __launch_bounds__(256)
-conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint, const float* __restrict__ w0,
+conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bool interior_done, const float* __restrict__ w0,
                       const float* __restrict__ gtv, float* __restrict__ img, float* __restrict__ exp_avg,
                       float* __restrict__ exp_avg_sq, float* __restrict__ ema, float* __restrict__ grad_out, int H,
                       int W, const AdamScalars* __restrict__ acp, int apply_update) {
@@ -147,13 +147,14 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
       wr[t][c].y = s_w[((2 * lane + 1) * 3 + c) * 9 + t];
     }
 
-  // with gint the interior pixels are updated by adam_interior_kernel; only strips that contain border pixels are
+  // interior_done: the interior pixels were updated by the tensor-core dgrad's epilogue (pixel GEMM mode 3); only
+  // strips that contain border pixels are
   // enumerated here: rows 0 and H-1 completely, first and last strip of every other row
   const int side = strips >= 2 ? 2 : 1;
-  const long total_items = gint ? ((long)2 * strips + (long)(H > 2 ? H - 2 : 0) * side) : total;
+  const long total_items = interior_done ? ((long)2 * strips + (long)(H > 2 ? H - 2 : 0) * side) : total;
   for (long wg = (long)blockIdx.x * 8 + (threadIdx.x >> 5); wg < total_items; wg += nwarps) {
     int y, xs;
-    if (!gint) {
+    if (!interior_done) {
       y = (int)(wg / strips);
       xs = (int)(wg % strips) * 32;
     } else if (wg < strips) {
@@ -181,16 +182,16 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int cidx = 0; cidx < 3; ++cidx)
-        win[r][cidx] = (gint == nullptr) ? ld(y - 1 + r, xs - 1 + cidx) : F2{0.f, 0.f};
+        win[r][cidx] = (!interior_done) ? ld(y - 1 + r, xs - 1 + cidx) : F2{0.f, 0.f};
     const bool row_interior = (y > 0) && (y < H - 1);
     const int xe = min(xs + 32, W);
-    // gint != nullptr: the zero-pad dgrad of the interior pixels was already computed on the tensor cores
+    // interior_done: the zero-pad dgrad of the interior pixels was already computed on the tensor cores
     // (pixel_gemm with conv0's weights zero-padded to 64 output channels); only border pixels (where replicate
     // padding folds extra taps onto the pixel) are evaluated here.
     const bool strip_has_border = !row_interior || xs == 0 || xe == W;
-    if (gint == nullptr || strip_has_border)
+    if (!interior_done || strip_has_border)
     for (int x = xs; x < xe; ++x) {
-      if (gint != nullptr && row_interior && x > 0 && x < W - 1) continue;
+      if (interior_done && row_interior && x > 0 && x < W - 1) continue;
       F2 nxt[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r) nxt[r] = ld(y - 1 + r, x + 2);  // prefetch the next window column
@@ -238,7 +239,7 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
 
     const int x = xs + lane;
     if (x < W) {
-      const bool from_tc = gint != nullptr && row_interior && x > 0 && x < W - 1;  // done by adam_interior_kernel
+      const bool from_tc = interior_done && row_interior && x > 0 && x < W - 1;  // done by the pixel GEMM's mode-3 epilogue
       for (int c = 0; c < 3 && !from_tc; ++c) {
         const size_t idx = ((size_t)c * H + y) * W + x;
         const float g = keep[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
@@ -254,38 +255,6 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bf16* __restrict__ gint
           exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
         }
       }
-    }
-  }
-}
-
-// Interior pixels: the conv0 dgrad already sits in gint (bf16 NHWC, channels 0..2 valid) from the tensor cores; this
-// is the pure HBM-bound tail: Normalize backward + TV gradient + Adam + clamp + EMA, one thread per pixel.
-__global__ void __launch_bounds__(256)
-adam_interior_kernel(const bf16* __restrict__ gint, const float* __restrict__ gtv, float* __restrict__ img,
-                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ ema,
-                     float* __restrict__ grad_out, int H, int W, const AdamScalars* __restrict__ acp,
-                     int apply_update) {
-  AdamScalars ac{};
-  if (apply_update) ac = *acp;  // written on the device by adam_scalars_kernel (CUDA-graph friendly)
-  const int y = blockIdx.y + 1;
-  const int x = blockIdx.x * 256 + threadIdx.x + 1;
-  if (y >= H - 1 || x >= W - 1) return;
-  const uint2 u = __ldg(reinterpret_cast<const uint2*>(gint + ((size_t)y * W + x) * 64));
-  const float tcg[3] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y)};
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const size_t idx = ((size_t)c * H + y) * W + x;
-    const float g = tcg[c] / c_std[c] + (gtv ? gtv[idx] : 0.f);
-    if (grad_out) grad_out[idx] = g;
-    if (apply_update) {
-      float m = exp_avg[idx], v = exp_avg_sq[idx], p = img[idx], e = ema[idx];
-      m = m + (g - m) * ac.one_minus_b1;
-      v = v * ac.b2 + ac.one_minus_b2 * g * g;
-      const float denom = sqrtf(v) * ac.inv_sqrt_bc2 + ac.eps;
-      p = p - ac.step_size * (m / denom);
-      p = fminf(fmaxf(p, 0.f), 1.f);
-      e = e * ac.ema_decay + ac.one_minus_decay * p;
-      exp_avg[idx] = m; exp_avg_sq[idx] = v; img[idx] = p; ema[idx] = e;
     }
   }
 }
@@ -460,20 +429,16 @@ int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s) {
   return STB_OK;
 }
 
-int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
+int launch_conv0_bwd_adam(const bf16* g0, bool interior_done, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
                           const AdamScalars* a, int apply_update, cudaStream_t s) {
   const int strips = (W + 31) / 32;
-  const long warps = gint ? (2l * strips + (long)(H > 2 ? H - 2 : 0) * (strips >= 2 ? 2 : 1)) : (long)H * strips;
-  if (gint && H > 2 && W > 2) {
-    dim3 grid((W - 2 + 255) / 256, H - 2);
-    adam_interior_kernel<<<grid, 256, 0, s>>>(gint, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a, apply_update);
-  }
+  const long warps = interior_done ? (2l * strips + (long)(H > 2 ? H - 2 : 0) * (strips >= 2 ? 2 : 1)) : (long)H * strips;
   long want = (warps + 7) / 8;
   const long cap = (long)num_sms() * 2 * 4;  // persistent: a few waves of 8-warp CTAs
   const int blocks = (int)(want < cap ? want : cap);
-  conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, gint, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W, a,
-                                               apply_update);
+  conv0_bwd_adam_kernel<<<blocks, 256, 0, s>>>(g0, interior_done, w0, gtv, img, exp_avg, exp_avg_sq, ema, grad_out, H, W,
+                                               a, apply_update);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }

@@ -17,6 +17,8 @@ typedef __nv_bfloat16 bf16;
 //   bwd  (mode 1): + bias[n] (rows in [row_lo,row_hi)), + cscale*(y - ctarget), * (y > 0)
 //                                                         (conv dgrad + tap-gradient GEMM + ReLU mask; autograd of ST:475)
 //   lin  (mode 2): none (dgrad whose consumer is the pool backward)
+//   img  (mode 3): conv0 dgrad (Cout = 3, run as N = 16) whose epilogue IS the optimiser step of the interior pixels:
+//                  Normalize backward + TV gradient + Adam + clamp + EMA on the fp32 image state (ST:481-486)
 struct PixelGemmArgs {
   int H = 0, W = 0;
   int Cin = 0;    // main 3x3 source channels (multiple of 64) or 0
@@ -34,6 +36,11 @@ struct PixelGemmArgs {
   const bf16* ctarget = nullptr;  // bwd, optional: [H][W][Cout]
   float cscale = 0.f;
   int row_lo = 0, row_hi = 1 << 30;  // rows where bias (bwd) / content term apply
+  // mode 3 only: image-space state, all fp32 NCHW [3][H][W]; adam is a DEVICE pointer (see AdamScalars)
+  const float* gtv = nullptr;
+  float *img = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *ema = nullptr, *grad_out = nullptr;
+  const struct AdamScalars* adam = nullptr;
+  int apply_update = 0;
 };
 int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream);
 
@@ -53,10 +60,10 @@ int pack_weights_conv0_fwd(const float* w0, bf16* out, cudaStream_t s);
 // conv0 forward on tcgen05 with the im2col rows built in shared memory (conv0_tc.cu); out: bf16 NHWC [H][W][64]
 int launch_conv0_fwd(const float* img, const bf16* w0_packed, const float* bias, bf16* out, int H, int W,
                      cudaStream_t s);
-// g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  gint (optional): zero-pad dgrad of g0
-// through conv0 computed on the tensor cores, bf16 NHWC [H][W][64] with channels 0..2 valid (interior pixels are
-// taken from it, border pixels are evaluated here).  grad_out (optional) receives d loss/d image.
-int launch_conv0_bwd_adam(const bf16* g0, const bf16* gint, const float* w0, const float* gtv, float* img,
+// g0: masked gradient w.r.t. conv0's pre-activation, bf16 NHWC [H][W][64].  interior_done: the interior pixels were
+// already updated by the tensor-core dgrad (pixel GEMM mode 3); only the border pixels, where the adjoint of the
+// replicate pad folds extra taps onto the pixel, are evaluated here.  grad_out (optional) receives d loss/d image.
+int launch_conv0_bwd_adam(const bf16* g0, bool interior_done, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
                           const AdamScalars* d_adam, int apply_update, cudaStream_t s);  // d_adam: DEVICE pointer
 // conv0 dgrad weights for the tensor-core path: fp32 OIHW [64][3][3][3] -> bf16 [9][64 (ci, 3 real)][64 (co)]
