@@ -352,7 +352,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
     if (i == 0) {
       ctx->w0 = (float*)take(64 * 27 * 4);
       STB_CUDA_CHECK(cudaMemcpyAsync(ctx->w0, conv_w[0], 64 * 27 * 4, cudaMemcpyDeviceToDevice, s));
-      ctx->wb[0] = (bf16*)take((size_t)9 * 64 * 64 * 2);
+      ctx->wb[0] = (bf16*)take((size_t)32 * 64 * 2);
       STB_TRY(pack_weights_conv0_bwd(ctx->w0, ctx->wb[0], s));
       ctx->wf[0] = (bf16*)take((size_t)64 * 64 * 2);
       STB_TRY(pack_weights_conv0_fwd(ctx->w0, ctx->wf[0], s));
@@ -575,20 +575,14 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
       cur ^= 1;
     }
   }
-  // conv0 dgrad of the interior pixels on the tensor cores (N = 16, 3 used) with the optimiser step as its
-  // epilogue; the border pixels (adjoint of the replicate pad) and their update in SIMT
-  {
-    PixelGemmArgs a;
-    a.H = H; a.W = W; a.Cin = 64; a.Cout = 16; a.mode = 3;
-    a.A = g[cur]; a.Bw = ctx->wb[0];
-    a.gtv = at<float>(ctx, pl.gtv_off); a.img = img; a.exp_avg = exp_avg; a.exp_avg_sq = exp_avg_sq; a.ema = ema;
-    a.grad_out = grad_out; a.adam = d_adam; a.apply_update = apply_update;
-    ctx->prof.begin(PC_CONV0_BWD_ADAM, s);
-    STB_TRY(launch_pixel_gemm(a, s));
-    STB_TRY(launch_conv0_bwd_adam(g[cur], true, ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
-                                  grad_out, H, W, d_adam, apply_update, s));
-    ctx->prof.end(s);
-  }
+  // conv0 backward: interior pixels on the tensor cores (1x1 GEMM + col2im) with the optimiser step as epilogue;
+  // the border pixels (adjoint of the replicate pad) and their update in SIMT
+  ctx->prof.begin(PC_CONV0_BWD_ADAM, s);
+  STB_TRY(launch_conv0_bwd_interior(g[cur], ctx->wb[0], at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
+                                    grad_out, H, W, d_adam, apply_update, s));
+  STB_TRY(launch_conv0_bwd_adam(g[cur], true, ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
+                                grad_out, H, W, d_adam, apply_update, s));
+  ctx->prof.end(s);
   ctx->prof.begin(PC_FINALIZE, s);
   finalize_loss_kernel<<<1, 32, 0, s>>>(at<float>(ctx, pl.stats_off) + pl.stats_scalars,
                                         ctx->content_weight / (float)n22, loss_dev + 16, ctx->tv_weight, loss_dev);

@@ -55,17 +55,14 @@ int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void*
 
 int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
                        void* stream) {
-  // product path: interior via the tcgen05 dgrad (N = 16) with the image-space epilogue, borders in SIMT
+  // product path: interior via the tcgen05 1x1 GEMM + col2im kernel with the image-space epilogue, borders in SIMT
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bf16* wp = nullptr;
-  STB_CUDA_CHECK(cudaMalloc(&wp, 9 * 64 * 64 * 2));
+  STB_CUDA_CHECK(cudaMalloc(&wp, 32 * 64 * 2));
   int rc = pack_weights_conv0_bwd(w0, wp, s);
-  if (rc == 0) {
-    PixelGemmArgs a;
-    a.H = H; a.W = W; a.Cin = 64; a.Cout = 16; a.mode = 3;
-    a.A = static_cast<const bf16*>(g0_bf16); a.Bw = wp; a.gtv = gtv; a.grad_out = grad_out;
-    rc = launch_pixel_gemm(a, s);
-  }
+  if (rc == 0)
+    rc = launch_conv0_bwd_interior(static_cast<const bf16*>(g0_bf16), wp, gtv, nullptr, nullptr, nullptr, nullptr,
+                                   grad_out, H, W, nullptr, 0, s);
   if (rc == 0)
     rc = launch_conv0_bwd_adam(static_cast<const bf16*>(g0_bf16), true, w0, gtv, nullptr, nullptr, nullptr, nullptr,
                                grad_out, H, W, nullptr, 0, s);

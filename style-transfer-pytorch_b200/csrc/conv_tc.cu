@@ -35,7 +35,7 @@ template <int BN>
 struct Cfg {
   static constexpr int MT = BN == 256 ? 1 : 2;
   static constexpr int NA = 3;
-  static constexpr int NB = BN <= 64 ? 8 : 4;
+  static constexpr int NB = BN == 64 ? 8 : 4;
   static constexpr int A_PITCH = MT * 1024;                 // bytes per row of 8*MT pixels
   static constexpr int A_STAGE_BYTES = A_ROWS * A_PITCH;    // dx buffer: 18 rows x 8*MT px x 64 ch
   static constexpr int A2_BYTES = TILE_H * A_PITCH;         // centre box for the 1x1 source
@@ -61,14 +61,7 @@ struct KParams {
   const bf16* ctarget;
   float cscale;
   int row_lo, row_hi;
-  // MODE 3
-  const float* gtv;
-  float *img, *exp_avg, *exp_avg_sq, *ema, *grad_out;
-  const AdamScalars* adam;
-  int apply_update;
 };
-
-__constant__ float c_inv_std[3] = {(float)(1.0 / 0.229), (float)(1.0 / 0.224), (float)(1.0 / 0.225)};
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -228,91 +221,11 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t pacc = 0;
     int stg = 0;
-    if constexpr (MODE == 3) {
-      // conv0 dgrad: columns 0..2 of the accumulator are d loss / d (normalised pixel); the optimiser step of the
-      // interior pixels happens right here (border pixels: conv0_bwd_adam_kernel, which folds the replicate pad).
-      // The image-space state does not depend on the accumulator: the (32-byte-segment) loads of the fp32 planes
-      // for tile i+1 are issued before tile i is processed -- two register sets, manually ping-ponged -- so their
-      // DRAM latency hides behind a whole tile of MMAs instead of serialising with the epilogue.
-      struct State {
-        float tv[C::MT][3], m[C::MT][3], v[C::MT][3], p[C::MT][3], e[C::MT][3];
-      };
-      AdamScalars ac{};
-      if (p.apply_update) ac = *p.adam;
-      auto prefetch = [&](int tile, State& S) {
-        const int t2 = tile / p.n_tiles_n;
-        const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-#pragma unroll
-        for (int m = 0; m < C::MT; ++m) {
-          const int py = ty * TILE_H + (r >> 3), px = (tx * C::MT + m) * TILE_W + (r & 7);
-          const bool interior = py > 0 && py < p.H - 1 && px > 0 && px < p.W - 1;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const size_t idx = (static_cast<size_t>(c) * p.H + py) * p.W + px;
-            S.tv[m][c] = (interior && p.gtv) ? __ldg(p.gtv + idx) : 0.f;
-            const bool ld = interior && p.apply_update;
-            S.m[m][c] = ld ? p.exp_avg[idx] : 0.f;
-            S.v[m][c] = ld ? p.exp_avg_sq[idx] : 0.f;
-            S.p[m][c] = ld ? p.img[idx] : 0.f;
-            S.e[m][c] = ld ? p.ema[idx] : 0.f;
-          }
-        }
-      };
-      auto process = [&](int tile, const State& S) {
-        const int t2 = tile / p.n_tiles_n;
-        const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-        mbar_wait(&t_full[acc], pacc);
-        tc_fence_after();
-#pragma unroll
-        for (int m = 0; m < C::MT; ++m) {
-          const int py = ty * TILE_H + (r >> 3), px = (tx * C::MT + m) * TILE_W + (r & 7);
-          uint32_t v[4];
-          tmem_ld_32x32_x4(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + (acc * C::MT + m) * BN, v);
-          tmem_ld_wait();
-          if (py > 0 && py < p.H - 1 && px > 0 && px < p.W - 1) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const size_t idx = (static_cast<size_t>(c) * p.H + py) * p.W + px;
-              const float g = __uint_as_float(v[c]) * c_inv_std[c] + S.tv[m][c];
-              if (p.grad_out) p.grad_out[idx] = g;
-              if (p.apply_update) {
-                float mm = S.m[m][c], vv = S.v[m][c], pp = S.p[m][c], ee = S.e[m][c];
-                mm = mm + (g - mm) * ac.one_minus_b1;
-                vv = vv * ac.b2 + ac.one_minus_b2 * g * g;
-                const float denom = sqrtf(vv) * ac.inv_sqrt_bc2 + ac.eps;
-                pp = pp - ac.step_size * (mm / denom);
-                pp = fminf(fmaxf(pp, 0.f), 1.f);
-                ee = ee * ac.ema_decay + ac.one_minus_decay * pp;
-                p.exp_avg[idx] = mm; p.exp_avg_sq[idx] = vv; p.img[idx] = pp; p.ema[idx] = ee;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
-      };
-      State S0, S1;
-      int tile = blockIdx.x;
-      const int step = gridDim.x;
-      if (tile < p.total_tiles) prefetch(tile, S0);
-      while (tile < p.total_tiles) {
-        if (tile + step < p.total_tiles) prefetch(tile + step, S1);
-        process(tile, S0);
-        tile += step;
-        if (tile >= p.total_tiles) break;
-        if (tile + step < p.total_tiles) prefetch(tile + step, S0);
-        process(tile, S1);
-        tile += step;
-      }
-    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int tn = tile % p.n_tiles_n;
       const int t2 = tile / p.n_tiles_n;
       const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
       const int y0 = ty * TILE_H, n0 = tn * BN;
-      {
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
@@ -398,7 +311,6 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         stg ^= 1;
       }
-      }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -434,11 +346,10 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 
 int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   STB_CHECK(a.H > 0 && a.W > 0, STB_ERR_INVALID, "pixel_gemm: bad spatial size %dx%d", a.H, a.W);
-  STB_CHECK((a.Cout % 64 == 0 && a.Cout <= 512) || (a.mode == 3 && a.Cout == 16), STB_ERR_INVALID,
-            "pixel_gemm: Cout=%d", a.Cout);
+  STB_CHECK(a.Cout % 64 == 0 && a.Cout <= 512, STB_ERR_INVALID, "pixel_gemm: Cout=%d", a.Cout);
   STB_CHECK(a.Cin % 64 == 0 && a.C2 % 64 == 0 && (a.Cin + a.C2) > 0, STB_ERR_INVALID, "pixel_gemm: Cin=%d C2=%d",
             a.Cin, a.C2);
-  const int BN = a.Cout >= 256 ? 256 : a.Cout;  // 16 only for mode 3
+  const int BN = a.Cout >= 256 ? 256 : a.Cout;
   KParams kp;
   kp.H = a.H; kp.W = a.W; kp.Cin = a.Cin; kp.Cout = a.Cout; kp.C2 = a.C2;
   const int MT = BN == 256 ? 1 : 2;  // must match Cfg<BN>::MT
@@ -450,23 +361,11 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   kp.a2_row0 = a.a2_row0;
   kp.bias = a.bias; kp.mask_src = a.mask_src; kp.ctarget = a.ctarget; kp.cscale = a.cscale;
   kp.row_lo = a.row_lo; kp.row_hi = a.row_hi;
-  STB_CHECK(a.mode >= 0 && a.mode <= 3, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
+  STB_CHECK(a.mode >= 0 && a.mode <= 2, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
   if (a.mode == 1) STB_CHECK(a.mask_src != nullptr, STB_ERR_INVALID, "pixel_gemm: bwd needs mask_src");
-  kp.gtv = a.gtv; kp.img = a.img; kp.exp_avg = a.exp_avg; kp.exp_avg_sq = a.exp_avg_sq; kp.ema = a.ema;
-  kp.grad_out = a.grad_out; kp.adam = a.adam; kp.apply_update = a.apply_update;
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmOut;
   const uint64_t W = a.W, H = a.H;
-  if (a.mode == 3) {
-    // conv0 dgrad + optimiser epilogue: A = g0 [H][W][64]; B = the 64-row dgrad weight blocks of
-    // pack_weights_conv0_bwd, of which only rows 0..15 (3 real image channels) are fetched; no output tensor
-    STB_CHECK(a.Cin == 64 && a.C2 == 0 && (!a.apply_update || (a.adam && a.img && a.exp_avg && a.exp_avg_sq && a.ema)),
-              STB_ERR_INVALID, "pixel_gemm: mode 3 arguments");
-    STB_TRY(make_tmap_bf16_3d(&tmA, a.A, 64, W, H, 128ull, W * 128ull, 64, tile_w, A_ROWS));
-    STB_TRY(make_tmap_bf16_3d(&tmB, a.Bw, 64, 64, 9, 128ull, 64ull * 128ull, 64, 16, 1));
-    tmA2 = tmB2 = tmOut = tmA;
-    return launch_cfg<16, 3>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-  }
   // output first; unused maps alias it so that every descriptor handed to the kernel is valid
   STB_TRY(make_tmap_bf16_3d(&tmOut, a.out, a.Cout, W, H, a.Cout * 2ull, W * a.Cout * 2ull, 64, TILE_W, TILE_H));
   tmA = tmB = tmA2 = tmB2 = tmOut;
@@ -511,21 +410,6 @@ __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ ou
 }
 }  // namespace
 
-namespace {
-__global__ void pack_w0_bwd_kernel(const float* __restrict__ w0, bf16* __restrict__ out) {
-  // out[tap][ci][co] = w0[co][ci][8 - tap] for ci < 3, else 0
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * 64 * 64; i += gridDim.x * blockDim.x) {
-    const int co = i & 63, ci = (i >> 6) & 63, tap = i >> 12;
-    out[i] = __float2bfloat16(ci < 3 ? w0[(co * 3 + ci) * 9 + (8 - tap)] : 0.f);
-  }
-}
-}  // namespace
-
-int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s) {
-  pack_w0_bwd_kernel<<<64, 256, 0, s>>>(w0, out);
-  STB_CUDA_CHECK(cudaGetLastError());
-  return STB_OK;
-}
 
 int pack_weights_fwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
   pack_w_kernel<<<256, 256, 0, s>>>(w, out, Cout, Cin, 0);

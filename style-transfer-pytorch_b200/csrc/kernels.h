@@ -17,8 +17,6 @@ typedef __nv_bfloat16 bf16;
 //   bwd  (mode 1): + bias[n] (rows in [row_lo,row_hi)), + cscale*(y - ctarget), * (y > 0)
 //                                                         (conv dgrad + tap-gradient GEMM + ReLU mask; autograd of ST:475)
 //   lin  (mode 2): none (dgrad whose consumer is the pool backward)
-//   img  (mode 3): conv0 dgrad (Cout = 3, run as N = 16) whose epilogue IS the optimiser step of the interior pixels:
-//                  Normalize backward + TV gradient + Adam + clamp + EMA on the fp32 image state (ST:481-486)
 struct PixelGemmArgs {
   int H = 0, W = 0;
   int Cin = 0;    // main 3x3 source channels (multiple of 64) or 0
@@ -36,11 +34,6 @@ struct PixelGemmArgs {
   const bf16* ctarget = nullptr;  // bwd, optional: [H][W][Cout]
   float cscale = 0.f;
   int row_lo = 0, row_hi = 1 << 30;  // rows where bias (bwd) / content term apply
-  // mode 3 only: image-space state, all fp32 NCHW [3][H][W]; adam is a DEVICE pointer (see AdamScalars)
-  const float* gtv = nullptr;
-  float *img = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *ema = nullptr, *grad_out = nullptr;
-  const struct AdamScalars* adam = nullptr;
-  int apply_update = 0;
 };
 int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream);
 
@@ -66,8 +59,12 @@ int launch_conv0_fwd(const float* img, const bf16* w0_packed, const float* bias,
 int launch_conv0_bwd_adam(const bf16* g0, bool interior_done, const float* w0, const float* gtv, float* img,
                           float* exp_avg, float* exp_avg_sq, float* ema, float* grad_out, int H, int W,
                           const AdamScalars* d_adam, int apply_update, cudaStream_t s);  // d_adam: DEVICE pointer
-// conv0 dgrad weights for the tensor-core path: fp32 OIHW [64][3][3][3] -> bf16 [9][64 (ci, 3 real)][64 (co)]
+// conv0 backward on tcgen05 (conv0_tc.cu): weights fp32 OIHW [64][3][3][3] -> bf16 [32 (ky,kx,c; 27 used)][64 co];
+// the kernel updates the interior pixels (1x1 GEMM + col2im in smem + Normalize bwd + TV grad + Adam + clamp + EMA)
 int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s);
+int launch_conv0_bwd_interior(const bf16* g0, const bf16* w0q, const float* gtv, float* img, float* exp_avg,
+                              float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars* d_adam,
+                              int apply_update, cudaStream_t s);
 int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s);
 int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s);
 int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s);
