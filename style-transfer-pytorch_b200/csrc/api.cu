@@ -203,20 +203,18 @@ int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool 
   int np = 0;
   const bf16* cur = at<bf16>(ctx, pl.act_off[0]);
   for (int i = 1; i <= last_conv; ++i) {
-    if (kPoolAfter[i - 1]) {
-      bf16* po = at<bf16>(ctx, pl.pool_off[np++]);
-      ctx->prof.begin(PC_POOL_FWD, s);
-      STB_TRY(launch_pool_fwd(ctx->pooling, cur, po, pl.h[i - 1], pl.w[i - 1], kCout[i - 1], s));
-      ctx->prof.end(s);
-      cur = po;
-    }
     PixelGemmArgs a;
     a.H = pl.h[i]; a.W = pl.w[i]; a.Cin = kCin[i]; a.Cout = kCout[i]; a.mode = 0;
     a.A = cur; a.Bw = ctx->wf[i]; a.out = at<bf16>(ctx, pl.act_off[i]); a.bias = ctx->bias[i];
+    cur = a.out;
+    if (kPoolAfter[i] && i < last_conv) {  // the 2x2 pool that follows this conv is produced by its epilogue
+      a.pool_out = at<bf16>(ctx, pl.pool_off[np++]);
+      a.pooling = ctx->pooling;
+      cur = a.pool_out;
+    }
     ctx->prof.begin(PC_CONV_FWD, s);
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
-    cur = a.out;
   }
   return STB_OK;
 }

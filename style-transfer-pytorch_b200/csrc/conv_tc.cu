@@ -26,6 +26,7 @@ namespace {
 constexpr int TILE_H = 16, TILE_W = 8;           // output pixels per sub-tile = 128 = UMMA M
 constexpr int A_ROWS = TILE_H + 2;               // dx buffer rows (halo above/below)
 constexpr int STG_BYTES = TILE_H * 1024;         // 128 pixels x 64 ch bf16 staging for the TMA store
+constexpr int PSTG_BYTES = (TILE_H / 2) * (TILE_W / 2) * 128;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 
@@ -45,7 +46,8 @@ struct Cfg {
   static constexpr int OFF_B = OFF_A + NA * A_STAGE_BYTES;
   static_assert(TMEM_COLS <= 512, "TMEM budget");
   static constexpr int OFF_STG = OFF_B + NB * B_STAGE_BYTES;
-  static constexpr int OFF_BIAS = OFF_STG + 2 * STG_BYTES;
+  static constexpr int OFF_PSTG = OFF_STG + 2 * STG_BYTES;  // 2 x 4 KiB: pooled 8x4-pixel tile of the fused 2x2 pool
+  static constexpr int OFF_BIAS = OFF_PSTG + 2 * PSTG_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + 512 * 4;
   static constexpr int NUM_BARS = 2 * NA + 2 * NB + 4;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
@@ -61,13 +63,15 @@ struct KParams {
   const bf16* ctarget;
   float cscale;
   int row_lo, row_hi;
+  int pooling;  // MODE 0: -1 = none, else STB_POOL_*: also emit the 2x2-pooled output (tmPool)
 };
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                  const __grid_constant__ CUtensorMap tmOut, const KParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool,
+                  const KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,6 +99,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB2);
     tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmPool);
     for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
@@ -305,9 +310,56 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         fence_proxy_async_smem();
         named_bar_sync(2, NUM_EPI_THREADS);
+        const bool pooled = (MODE == 0) && p.pooling >= 0;
         if (et == 0) {
           tma_store_3d(&tmOut, stage, n0 + j * 64, x0, y0);
-          tma_store_commit();
+          if (!pooled) tma_store_commit();
+        }
+        if (MODE == 0 && pooled) {
+          // fused 2x2 / stride-2 pool (ST:21-22, 41-46) of the tile just staged: 8 x 4 pooled pixels x 8 chunks of
+          // 8 channels = 256 tasks; windows never straddle tiles (tile origin and size are even)
+          uint8_t* pst = smem + C::OFF_PSTG + stg * PSTG_BYTES;
+#pragma unroll
+          for (int task = et; task < 256; task += NUM_EPI_THREADS) {
+            const int pp = task >> 3, c16 = task & 7;
+            const int r0 = ((pp >> 2) * 2) * TILE_W + (pp & 3) * 2;  // top-left source pixel (row of the tile)
+            uint4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int rr = r0 + (q >> 1) * TILE_W + (q & 1);
+              v[q] = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float lo[4], hi[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t u = reinterpret_cast<const uint32_t*>(&v[q])[k];
+                lo[q] = bf16lo(u);
+                hi[q] = bf16hi(u);
+              }
+              float a, b;
+              if (p.pooling == STB_POOL_MAX) {
+                a = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
+                b = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+              } else if (p.pooling == STB_POOL_AVERAGE) {
+                a = (lo[0] + lo[1] + lo[2] + lo[3]) * 0.25f * 2.0f;
+                b = (hi[0] + hi[1] + hi[2] + hi[3]) * 0.25f * 2.0f;
+              } else {
+                a = sqrtf(lo[0] * lo[0] + lo[1] * lo[1] + lo[2] * lo[2] + lo[3] * lo[3]) * 0.78f;
+                b = sqrtf(hi[0] * hi[0] + hi[1] * hi[1] + hi[2] * hi[2] + hi[3] * hi[3]) * 0.78f;
+              }
+              o[k] = pack_bf16x2(a, b);
+            }
+            *reinterpret_cast<uint4*>(pst + pp * 128 + ((c16 ^ (pp & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(3, NUM_EPI_THREADS);
+          if (et == 0) {
+            tma_store_3d(&tmPool, pst, n0 + j * 64, x0 >> 1, y0 >> 1);
+            tma_store_commit();
+          }
         }
         stg ^= 1;
       }
@@ -328,7 +380,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int BN, int MODE>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
-               const CUtensorMap& tmOut, const KParams& kp, cudaStream_t stream) {
+               const CUtensorMap& tmOut, const CUtensorMap& tmPool, const KParams& kp, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   auto kern = pixel_gemm_kernel<BN, MODE>;
@@ -337,7 +389,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     attr_set = true;
   }
   int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, tmOut, kp);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }
@@ -364,11 +416,19 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   STB_CHECK(a.mode >= 0 && a.mode <= 2, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
   if (a.mode == 1) STB_CHECK(a.mask_src != nullptr, STB_ERR_INVALID, "pixel_gemm: bwd needs mask_src");
 
-  CUtensorMap tmA, tmB, tmA2, tmB2, tmOut;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmOut, tmPool;
   const uint64_t W = a.W, H = a.H;
   // output first; unused maps alias it so that every descriptor handed to the kernel is valid
   STB_TRY(make_tmap_bf16_3d(&tmOut, a.out, a.Cout, W, H, a.Cout * 2ull, W * a.Cout * 2ull, 64, TILE_W, TILE_H));
-  tmA = tmB = tmA2 = tmB2 = tmOut;
+  tmA = tmB = tmA2 = tmB2 = tmPool = tmOut;
+  kp.pooling = -1;
+  if (a.pool_out != nullptr) {
+    STB_CHECK(a.mode == 0 && a.pooling >= 0 && a.pooling <= 2 && H >= 2 && W >= 2, STB_ERR_INVALID,
+              "pixel_gemm: fused pool needs mode 0 and a valid pooling");
+    kp.pooling = a.pooling;
+    STB_TRY(make_tmap_bf16_3d(&tmPool, a.pool_out, a.Cout, W / 2, H / 2, a.Cout * 2ull, (W / 2) * a.Cout * 2ull, 64,
+                              TILE_W / 2, TILE_H / 2));
+  }
   if (a.Cin > 0) {
     STB_TRY(make_tmap_bf16_3d(&tmA, a.A, a.Cin, W, H, a.Cin * 2ull, W * a.Cin * 2ull, 64, tile_w, A_ROWS));
     STB_TRY(make_tmap_bf16_3d(&tmB, a.Bw, a.Cin, a.Cout, 9, a.Cin * 2ull, (uint64_t)a.Cout * a.Cin * 2ull, 64, BN, 1));
@@ -379,17 +439,17 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
     STB_TRY(make_tmap_bf16_3d(&tmB2, a.B2, a.C2, a.Cout, 1, a.C2 * 2ull, (uint64_t)a.Cout * a.C2 * 2ull, 64, BN, 1));
   }
   if (a.mode == 0) {
-    if (BN == 256) return launch_cfg<256, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    if (BN == 128) return launch_cfg<128, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    return launch_cfg<64, 0>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+    if (BN == 256) return launch_cfg<256, 0>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    if (BN == 128) return launch_cfg<128, 0>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    return launch_cfg<64, 0>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
   } else if (a.mode == 1) {
-    if (BN == 256) return launch_cfg<256, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    if (BN == 128) return launch_cfg<128, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    return launch_cfg<64, 1>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+    if (BN == 256) return launch_cfg<256, 1>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    if (BN == 128) return launch_cfg<128, 1>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    return launch_cfg<64, 1>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
   } else {
-    if (BN == 256) return launch_cfg<256, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    if (BN == 128) return launch_cfg<128, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
-    return launch_cfg<64, 2>(tmA, tmB, tmA2, tmB2, tmOut, kp, stream);
+    if (BN == 256) return launch_cfg<256, 2>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    if (BN == 128) return launch_cfg<128, 2>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
+    return launch_cfg<64, 2>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp, stream);
   }
 }
 

@@ -166,19 +166,30 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-// sum partials in a fixed order (8 interleaved accumulators for memory-level parallelism, then a fixed tree):
-// out[i] = sum_s part[s][i]; deterministic run to run
+// sum partials in a fixed order (16 interleaved accumulators for memory-level parallelism, then a fixed tree):
+// out[i] = sum_s part[s][i]; deterministic run to run.  One launch covers the Gram partials (n0 elements) and the
+// channel-sum partials (n1 elements, element index continues after n0).
 __global__ void __launch_bounds__(256)
-gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int n_splits) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int k = 0;
-    for (; k + 8 <= n_splits; k += 8) {
+gram_reduce_kernel(const float* __restrict__ part0, float* __restrict__ out0, long n0,
+                   const float* __restrict__ part1, float* __restrict__ out1, long n1, int n_splits) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1; e += (long)gridDim.x * blockDim.x) {
+    const bool first = e < n0;
+    const float* part = first ? part0 : part1;
+    const long n = first ? n0 : n1, i = first ? e : e - n0;
+    float a[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += __ldg(part + (size_t)(k + u) * n + i);
+    for (int u = 0; u < 16; ++u) a[u] = 0.f;
+    int k = 0;
+    for (; k + 16 <= n_splits; k += 16) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a[u] += __ldg(part + (size_t)(k + u) * n + i);
     }
     for (; k < n_splits; ++k) a[0] += __ldg(part + (size_t)k * n + i);
-    out[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int u = 0; u < w; ++u) a[u] += a[u + w];
+    (first ? out0 : out1)[i] = a[0];
   }
 }
 
@@ -237,9 +248,8 @@ int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, 
   else if (BN == 128) STB_TRY(launch_gram_cfg<128>(tm, gp, n_ti * n_tj, n_splits, stream));
   else STB_TRY(launch_gram_cfg<64>(tm, gp, n_ti * n_tj, n_splits, stream));
   const long nn = (long)C * C;
-  int g = (int)((nn + 255) / 256);
-  gram_reduce_kernel<<<g, 256, 0, stream>>>(gp.partials, S_raw, nn, n_splits);
-  gram_reduce_kernel<<<(C + 255) / 256, 256, 0, stream>>>(gp.sum_partials, sums, C, n_splits);
+  const int g = (int)((nn + C + 255) / 256);
+  gram_reduce_kernel<<<g, 256, 0, stream>>>(gp.partials, S_raw, nn, gp.sum_partials, sums, C, n_splits);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }

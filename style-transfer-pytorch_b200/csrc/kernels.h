@@ -34,6 +34,8 @@ struct PixelGemmArgs {
   const bf16* ctarget = nullptr;  // bwd, optional: [H][W][Cout]
   float cscale = 0.f;
   int row_lo = 0, row_hi = 1 << 30;  // rows where bias (bwd) / content term apply
+  bf16* pool_out = nullptr;       // fwd, optional: [H/2][W/2][Cout], the 2x2/stride-2 pool of `out` (floor mode)
+  int pooling = -1;               // STB_POOL_* of pool_out
 };
 int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream);
 

@@ -21,6 +21,7 @@
 // symmetry (reading a non-mirrored product as its transpose) is not an option: it turns the error recursion of
 // the coupled iteration, E' = E/2, into E' = E - A^(1/2) E A^(-1/2) / 2, which explodes for the ill-conditioned
 // covariances of real activations (measured: NaN at 2048^2).  Tensor maps are encoded once per workspace binding.
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -119,6 +120,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+
+  // Programmatic dependent launch: the rounds are a chain of 52 dependent grids of <= 98 CTAs on 148 SMs.  Everything
+  // above (barrier init, TMEM allocation, descriptor prefetch) ran on idle SMs while the previous round was still
+  // computing; only from here on are its results touched.  Releasing our own dependents right after the wait keeps
+  // the run-ahead at exactly one round.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ---- TMA producer: four planes per stage
@@ -613,9 +621,20 @@ int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
     STB_CUDA_CHECK(cudaFuncSetAttribute(w2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES));
     attr_set = true;
   }
-  for (int r = r0; r < r1; ++r)
-    w2_gemm_kernel<<<rounds[r].n_tiles, T_THREADS, T_SMEM_BYTES, s>>>(rounds[r]);
-  STB_CUDA_CHECK(cudaGetLastError());
+  static const bool pdl = [] { const char* e = getenv("STB_PDL"); return !(e && e[0] == '0'); }();
+  for (int r = r0; r < r1; ++r) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(rounds[r].n_tiles);
+    cfg.blockDim = dim3(T_THREADS);
+    cfg.dynamicSmemBytes = T_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, w2_gemm_kernel, rounds[r]));
+  }
   return STB_OK;
 }
 
