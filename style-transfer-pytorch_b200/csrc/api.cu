@@ -102,9 +102,17 @@ struct stb_ctx {
     int H, W; const void *ws, *img, *m, *v, *ema, *loss; float lr, b1, b2, eps, decay;
     bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
   };
-  GraphKey gkey{};
-  int gkey_hits = 0;
-  cudaGraphExec_t gexec = nullptr;
+  struct GraphSlot {
+    GraphKey key{};
+    int hits = 0;
+    cudaGraphExec_t exec = nullptr;
+    void reset() {
+      if (exec) cudaGraphExecDestroy(exec);
+      exec = nullptr; key = GraphKey{}; hits = 0;
+    }
+  };
+  GraphSlot gslot[3];  // 0: stb_iterate, 1: stb_iterate_fwd, 2: stb_iterate_bwd (multi-GPU phases)
+  void reset_graphs() { for (auto& g : gslot) g.reset(); }
   bool graphs_enabled = true;
   bool band_on = false;
   int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
@@ -380,7 +388,7 @@ void stb_ctx_destroy(stb_ctx* ctx) {
   if (ctx->owned) cudaFree(ctx->owned);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+  ctx->reset_graphs();
   delete ctx;
 }
 
@@ -402,8 +410,7 @@ int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream) {
   STB_CUDA_CHECK(cudaStreamSynchronize(s));
   ctx->ws = static_cast<uint8_t*>(ptr);
   ctx->ws_bytes = bytes;
-  if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
-  ctx->gkey = stb_ctx::GraphKey{};
+  ctx->reset_graphs();
   ctx->targets_set = false;
   STB_TRY(ctx->w2.init(ctx->ws, ctx->w2_bytes, kStyleC));
   ctx->w2_ready = true;
@@ -458,8 +465,7 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
   make_plan(ctx, H, W, &pl);
   STB_TRY(ensure_ws(ctx, pl));
   STB_CHECK(ctx->w2_ready, STB_ERR_STATE, "workspace not bound");
-  if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }  // weights are baked into the graph
-  ctx->gkey = stb_ctx::GraphKey{};
+  ctx->reset_graphs();  // weights are baked into the graphs
   const size_t cbytes = (size_t)pl.h[kContentConv] * pl.w[kContentConv] * 512 * 2;
   STB_CUDA_CHECK(cudaMemcpyAsync(at<bf16>(ctx, pl.ctarget_off), content_target_bf16, cbytes, cudaMemcpyDeviceToDevice, s));
   float* stats = at<float>(ctx, pl.stats_off);
@@ -593,6 +599,44 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
 
 }  // namespace
 
+// ---- CUDA graphs: an iteration (or one of its multi-GPU phases) is ~50-110 launches with fixed arguments; replaying
+// a captured graph removes the per-launch host cost and the tensor-map encodes (matters most at the small pyramid
+// levels and when the image is tiled over many GPUs).  `key` holds everything that is baked into the launches.
+template <typename Run>
+int run_graphed(stb_ctx* ctx, int slot, const stb_ctx::GraphKey& key, bool allowed, cudaStream_t s, Run&& run) {
+  const bool legacy = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+  if (!ctx->graphs_enabled || ctx->prof.on || legacy || !allowed) return run();
+  stb_ctx::GraphSlot& g = ctx->gslot[slot];
+  if (!(key == g.key)) {
+    g.reset();
+    g.key = key;
+  }
+  if (g.exec) {
+    STB_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+    return STB_OK;
+  }
+  if (++g.hits < 3) return run();  // eager first (lazy one-time setup must not happen inside a capture)
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->graphs_enabled = false;
+    return run();
+  }
+  const int rc = run();
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc != STB_OK || ce != cudaSuccess || graph == nullptr ||
+      cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g.exec = nullptr;
+    ctx->graphs_enabled = false;  // fall back to eager launches for this context
+    return run();
+  }
+  cudaGraphDestroy(graph);
+  STB_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+  return STB_OK;
+}
+
 extern "C" {
 
 // One pass of ST:480-486.  apply_update = 0 evaluates loss / gradient only (test hook, L-BFGS closure).
@@ -624,42 +668,10 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
     adam_scalars_kernel<<<1, 1, 0, s>>>(ctx->d_step, ctx->d_adam, lr, beta1, beta2, adam_eps, ema_decay);
     return iterate_bwd(ctx, pl, img, exp_avg, exp_avg_sq, ema, ctx->d_adam, 1, grad_out, loss_out_host8, s);
   };
-  // ---- CUDA graph: an iteration is ~110 launches with fixed arguments; replaying a captured graph removes the
-  // per-launch host cost and the tensor-map encodes (matters most at the small pyramid levels)
-  const bool legacy = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
-  if (!ctx->graphs_enabled || ctx->prof.on || legacy || grad_out != nullptr) return run();
   stb_ctx::GraphKey key{};
   key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img; key.m = exp_avg; key.v = exp_avg_sq; key.ema = ema;
   key.loss = loss_out_host8; key.lr = lr; key.b1 = beta1; key.b2 = beta2; key.eps = adam_eps; key.decay = ema_decay;
-  if (!(key == ctx->gkey)) {
-    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
-    ctx->gkey = key;
-    ctx->gkey_hits = 0;
-  }
-  if (ctx->gexec) {
-    STB_CUDA_CHECK(cudaGraphLaunch(ctx->gexec, s));
-    return STB_OK;
-  }
-  if (++ctx->gkey_hits < 3) return run();  // eager first (lazy one-time setup must not happen inside a capture)
-  cudaGraph_t graph = nullptr;
-  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
-    cudaGetLastError();
-    ctx->graphs_enabled = false;
-    return run();
-  }
-  const int rc = run();
-  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-  if (rc != STB_OK || ce != cudaSuccess || graph == nullptr ||
-      cudaGraphInstantiate(&ctx->gexec, graph, 0) != cudaSuccess) {
-    cudaGetLastError();
-    if (graph) cudaGraphDestroy(graph);
-    ctx->gexec = nullptr;
-    ctx->graphs_enabled = false;  // fall back to eager launches for this context
-    return run();
-  }
-  cudaGraphDestroy(graph);
-  STB_CUDA_CHECK(cudaGraphLaunch(ctx->gexec, s));
-  return STB_OK;
+  return run_graphed(ctx, 0, key, grad_out == nullptr, s, run);
 }
 
 // ---- spatial tiling across GPUs: the host drives
@@ -692,7 +704,10 @@ int stb_iterate_fwd(stb_ctx* ctx, const float* img, void* stream) {
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
   STB_TRY(ensure_ws(ctx, pl));
-  return iterate_fwd(ctx, pl, img, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  stb_ctx::GraphKey key{};
+  key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img;
+  return run_graphed(ctx, 1, key, true, s, [&]() -> int { return iterate_fwd(ctx, pl, img, s); });
 }
 
 int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_host8, void* stream) {
@@ -701,8 +716,12 @@ int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_h
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
   STB_TRY(ensure_ws(ctx, pl));
-  return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad_out, loss_out_host8,
-                     static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  stb_ctx::GraphKey key{};
+  key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img; key.m = grad_out; key.loss = loss_out_host8;
+  return run_graphed(ctx, 2, key, true, s, [&]() -> int {
+    return iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad_out, loss_out_host8, s);
+  });
 }
 
 // Adam + clamp + EMA on rows [row0, row0+rows) of [3][H][W] fp32 tensors (the band's own rows)

@@ -5,8 +5,18 @@
 // split-K: CTA (tile, split) accumulates a 128 x BN fp32 tile in TMEM over its pixel range and writes a partial;
 // gram_reduce sums the partials in a fixed order (deterministic).
 //
+// Accuracy: the tensor core adds into its fp32 accumulator with TRUNCATION, and here every product is >= 0 (post-ReLU
+// features), so a chain of n k-steps loses ~n * 2^-24.5 of the sum -- systematically.  At 2048^2 the relu1_1 chain is
+// 1771 steps per CTA (-8e-5), which the covariance (S/N - mu mu^T) and the W2 cancellation amplify ~200x into a
+// -1 % error of that style term (measured: -0.27 % at 1024^2).  For C <= 128 the accumulator is therefore double
+// buffered in TMEM and DRAINED every 32 k-steps into fp32 registers of the epilogue warps (round-to-nearest adds),
+// which overlaps with the next chunk's MMAs and costs nothing on these HBM-bound layers.  C >= 256 (no TMEM room for
+// a second 256-column set) keeps one set; its chains are <= 221 steps and its style terms carry 4 % of the loss.
+//
 // Both operands are the SAME pixel-major smem tiles read "MN-major" (channel contiguous, SW128): no transpose is
 // ever materialised.  Channel sums ride along as one extra N=16 MMA per k-step against a constant tile of ones.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -30,9 +40,12 @@ struct GCfg {
   // + one atom of slack: with C = 64 the (ignored) upper 64 accumulator rows read one atom past the stage
   static constexpr int OFF_ONES = G_STAGES * STAGE_BYTES + ATOM_BYTES;
   static constexpr int OFF_BAR = OFF_ONES + 2048;
-  static constexpr int OFF_TMEMPTR = OFF_BAR + (2 * G_STAGES + 1) * 8;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + (2 * G_STAGES + 4) * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;
-  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
+  static constexpr bool DRAIN = BN <= 128;
+  static constexpr int SET_COLS = BN + 32;                    // BN Gram columns + 16 channel-sum columns (+ pad)
+  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 512 : 256);
+  static constexpr int CHUNK_STAGES = DRAIN ? 32 / (PK / 16) : (1 << 30);  // stages per 32-k-step chunk
 };
 
 struct GParams {
@@ -52,7 +65,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* empty = full + G_STAGES;
-  uint64_t* t_full = empty + G_STAGES;
+  uint64_t* t_full = empty + G_STAGES;  // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,7 +87,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmF);
     for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(t_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
@@ -111,6 +125,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
     int s = 0;
     uint32_t ph = 0, accum = 0;
     for (int k = 0; k < n_k; ++k) {
+      const int chunk = k / C::CHUNK_STAGES, set = chunk & 1;
+      const bool chunk_first = (k % C::CHUNK_STAGES) == 0, chunk_last = ((k + 1) % C::CHUNK_STAGES) == 0 || k == n_k - 1;
+      if (chunk_first) {
+        if (C::DRAIN) mbar_wait(&t_empty[set], ((chunk >> 1) & 1) ^ 1);  // the epilogue has drained this set
+        accum = 0;
+      }
+      const uint32_t tmem_d = tmem_base + set * C::SET_COLS;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (leader) {
@@ -120,44 +141,82 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GParams p) {
         const uint32_t a_lo = umma_desc_lo(a_addr, ATOM_BYTES), b_lo = umma_desc_lo(b_addr, ATOM_BYTES);
 #pragma unroll
         for (int ks = 0; ks < PK / 16; ++ks) {
-          umma_bf16_split(tmem_base, a_lo + ks * 128, hi_mn, b_lo + ks * 128, hi_mn, idesc_main, accum | (ks > 0));
+          umma_bf16_split(tmem_d, a_lo + ks * 128, hi_mn, b_lo + ks * 128, hi_mn, idesc_main, accum | (ks > 0));
           if (tj == 0)
-            umma_bf16_split(tmem_base + BN, a_lo + ks * 128, hi_mn, ones_lo, hi_mn, idesc_sum, accum | (ks > 0));
+            umma_bf16_split(tmem_d + BN, a_lo + ks * 128, hi_mn, ones_lo, hi_mn, idesc_sum, accum | (ks > 0));
         }
         umma_commit(&empty[s]);
+        if (chunk_last) umma_commit(&t_full[set]);
       }
       __syncwarp();
       accum = 1;
       if (++s == G_STAGES) { s = 0; ph ^= 1; }
     }
-    if (leader) umma_commit(t_full);
-    __syncwarp();
   } else {
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
-    mbar_wait(t_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const bool valid = r < m_valid;
     float* dst = p.partials + ((size_t)split * p.C + (i0 + r)) * p.C + j0;
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + cb, v);
-      tmem_ld_wait();
+    const int n_chunks = (n_k + C::CHUNK_STAGES - 1) / C::CHUNK_STAGES;
+    if constexpr (C::DRAIN) {
+      // drain every finished 32-k-step chunk into registers (fp32, round to nearest); the MMAs of the next chunk run
+      // into the other TMEM set meanwhile
+      float acc[BN];
+      float acc_sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int set = c & 1;
+        mbar_wait(&t_full[set], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + set * C::SET_COLS + (static_cast<uint32_t>(wq * 32) << 16);
+#pragma unroll
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + cb, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cb + i] += __uint_as_float(v[i]);
+        }
+        if (tj == 0) {
+          uint32_t v[4];
+          tmem_ld_32x32_x4(taddr + BN, v);
+          tmem_ld_wait();
+          acc_sum += __uint_as_float(v[0]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[set]);
+      }
       if (valid && n_k > 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(dst + cb + 4 * q) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                          __uint_as_float(v[4 * q + 3]));
+        for (int q = 0; q < BN / 4; ++q)
+          *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        if (tj == 0) p.sum_partials[(size_t)split * p.C + i0 + r] = acc_sum;
       }
-    }
-    if (tj == 0) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + BN, v);
-      tmem_ld_wait();
-      if (valid && n_k > 0) p.sum_partials[(size_t)split * p.C + i0 + r] = __uint_as_float(v[0]);
+    } else {
+      if (n_chunks > 0) mbar_wait(&t_full[0], 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        if (valid && n_k > 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + cb + 4 * q) =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      if (tj == 0) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + BN, v);
+        tmem_ld_wait();
+        if (valid && n_k > 0) p.sum_partials[(size_t)split * p.C + i0 + r] = __uint_as_float(v[0]);
+      }
     }
     tc_fence_before();
   }
@@ -217,6 +276,11 @@ int gram_num_splits(long P, int C) {
   const int n_tiles = ((C + 127) / 128) * (C / BN);
   long chunks = (P + PK - 1) / PK;
   long want = (num_sms() + n_tiles - 1) / n_tiles;  // one CTA per SM
+  if (BN == 256) want *= 2;  // no TMEM room to drain (see gram_kernel): halve the truncating accumulation chains instead
+  {  // diagnostic knob: a different split count = a different (equally valid) fp32 summation order of the Gram
+    static const int div = [] { const char* e = getenv("STB_GRAM_SPLIT_DIV"); return e ? atoi(e) : 1; }();
+    if (div > 1) want = (want + div - 1) / div;
+  }
   if (want > chunks) want = chunks;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;

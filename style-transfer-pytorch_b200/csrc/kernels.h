@@ -78,16 +78,16 @@ size_t gram_partials_floats(long P, int C);
 int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
 
 // ---------------------------------------------------------------- W2 style loss engine (w2_tc.cu)
-// Every matrix of the chain is a (hi, lo) pair of fp32 planes, lo stored n*n floats after hi (3xTF32 split).
-struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major plane pairs, B symmetric
+// Every matrix of the chain is 4 fp32 planes of n*n floats: hi, lo (3xTF32 split) and the same for its transpose.
+struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major; a matrix = planes hi, lo, hi^T, lo^T
   const CUtensorMap* amap;  // [hi, lo] tensor maps of A with 128-row boxes (device memory)
-  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B with 64-row boxes
-  const CUtensorMap* dmap;  // [hi, lo, hi, lo] tensor maps of D for the TMA stores: 128-row boxes, 64-row boxes
+  const CUtensorMap* bmap;  // [hi, lo] tensor maps of B^T with 64-row boxes
+  const CUtensorMap* dmap;  // [hi, lo] tensor maps of D for the TMA stores (128-row boxes)
   float* D;
   float* red_out;  // optional: per-tile {sum of squares, trace} of D
   int n;
   float alpha, gamma;
-  int sym;  // D is symmetric: only upper tiles are scheduled, every value is stored to (i,j) and (j,i)
+  int write_t;  // also write the planes of D^T (D is later used as a right factor)
 };
 constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152;
 struct W2Round {  // one grouped launch; travels as a __grid_constant__ kernel parameter (no dependent global loads)

@@ -12,15 +12,21 @@
 // GEMM only ever streams ready-made planes through TMA.
 //
 // All five layers advance in lock-step: one "round" = one grouped launch whose CTAs are 128 x 64 output tiles of
-// every layer's GEMM (<= 98 CTAs, one wave).  Both tcgen05 operands are K-major SW128 tiles: A[m][k] from the
-// row-major planes of A and B[n][k] = B^T from the planes of B, which is only the same thing because every right
-// factor on this path is EXACTLY symmetric: cov, the Newton-Schulz iterates Y/Z/T, the Lyapunov iterates a/q/E and
-// P are all symmetric in exact arithmetic, and their producers enforce it bit-for-bit -- a symmetric result is
-// computed on the tiles that touch the upper triangle only (62 % of them at C=512) and each value is stored to
-// (i,j) and (j,i); the mirrored store is coalesced across the warp because TMEM lane = row.  Merely ASSUMING
-// symmetry (reading a non-mirrored product as its transpose) is not an option: it turns the error recursion of
-// the coupled iteration, E' = E/2, into E' = E - A^(1/2) E A^(-1/2) / 2, which explodes for the ill-conditioned
-// covariances of real activations (measured: NaN at 2048^2).  Tensor maps are encoded once per workspace binding.
+// every layer's GEMM (75 or 150 CTAs, largest matrices first).  Both tcgen05 operands are K-major SW128 tiles:
+// A[m][k] from the row-major planes of A, B[n][k] from the planes of B^T -- every matrix that is later used as a
+// right factor is therefore written TWICE by its producer: the planes of D (TMA store of the staged tile) and the
+// planes of D^T (scalar stores, coalesced across the warp because TMEM lane = row).
+//
+// The products are formed in exactly the reference's order, Y <- Y T, Z <- T Z, and NOTHING is symmetrised, although
+// every matrix here is symmetric in exact arithmetic.  Two shortcuts were tried and measured to break parity on real
+// (ill-conditioned, eps = 1e-4) covariances, where the coupled Newton-Schulz iteration amplifies a perturbation of
+// the small-eigenvalue directions by 1.5^12:
+//   * reading a computed product as its own transpose turns the error recursion E' = E/2 into
+//     E' = E - A^(1/2) E A^(-1/2) / 2: NaN at 2048^2;
+//   * computing only the upper triangle and mirroring it bit-for-bit (38 % fewer tiles) is stable but biases the
+//     style terms by -1e-3 ... -3e-3 at 512^2 and above (the CPU emulation of that schedule in fp32 shows the same),
+//     i.e. above the 1e-3 loss bar.  The full products stay within 3e-4 of the fp64 chain.
+// Tensor maps are encoded once per workspace binding.
 #include <cstdlib>
 #include <map>
 #include <vector>
@@ -34,10 +40,9 @@ namespace {
 
 constexpr int TM = 128, TN = 64, TKF = 32;      // tile rows / cols, k floats per stage (128 B swizzle row)
 constexpr int T_STAGES = 4;
-constexpr int T_CHUNK = 4;                         // stages (128 k) per hi*hi accumulator
-constexpr int T_MAX_CHUNKS = 4;                    // n <= 512
-constexpr int T_TMEM_COLS = 512;                   // 4 x 64 hi*hi chunk accumulators + 64 for the cross terms
-constexpr int T_CROSS_COL = T_MAX_CHUNKS * TN;
+constexpr int T_MAX_ACC = 6;                       // hi*hi accumulators: the K8 steps are dealt out to them in runs
+constexpr int T_TMEM_COLS = 512;                   // 6 x 64 hi*hi accumulators + 64 for the cross terms
+constexpr int T_CROSS_COL = T_MAX_ACC * TN;
 constexpr int A_PLANE_BYTES = TM * 128;          // 16 KiB
 constexpr int B_PLANE_BYTES = TN * 128;          // 8 KiB
 constexpr int T_STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 48 KiB
@@ -74,23 +79,10 @@ __device__ __forceinline__ void store_split(float* m, size_t nn, size_t e, float
 }
 __device__ __forceinline__ float load2(const float* m, size_t nn, size_t e) { return m[e] + m[nn + e]; }
 
-// D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 2 planes of n*n floats: hi, lo.
-// smem per stage: A planes [128 rows][32 k] and B planes [64 rows (n)][32 k] (B symmetric), all K-major SW128.
-//
-// Symmetric results and the 128 x 64 tiling.  With tile (ti, tj) covering rows [128 ti, +128) and columns [64 tj, +64):
-//   tj == 2 ti      ("A"): rows 0..63 are a self-mirroring 64 x 64 diagonal block, rows 64..127 lie below the diagonal
-//                          and are NOT stored (tile (ti, 2ti+1) mirrors into them);
-//   tj == 2 ti + 1  ("B"): rows 0..63 are strictly above the diagonal (stored + mirrored), rows 64..127 are a
-//                          self-mirroring diagonal block;
-//   tj >  2 ti + 1       : strictly above the diagonal: stored + mirrored;      tj < 2 ti: not scheduled.
-// Inside a diagonal block the value of (i,j), j < i, is taken from the accumulator of (j,i) through shared memory, so
-// the stored matrix is symmetric bit-for-bit.
-__host__ __device__ __forceinline__ bool tile_in_upper(int ti, int tj) { return tj >= 2 * ti; }
-static_assert(TM == 2 * TN, "tile classes above assume 128 x 64 tiles");
-
-constexpr int S_PITCH = TN + 1;                     // raw fp32 tile [128][65] in the (drained) stage-0 buffer
-constexpr int STG_OFF = T_STAGE_BYTES;              // 4 store tiles (2 column halves x hi/lo) of 16 KiB, SW128
-static_assert(TM * S_PITCH * 4 <= T_STAGE_BYTES && STG_OFF + 4 * A_PLANE_BYTES <= T_STAGES * T_STAGE_BYTES, "epilogue smem");
+// D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 4 planes of n*n floats: hi, lo, hi^T, lo^T.
+// smem per stage: A planes [128 rows][32 k] and B^T planes [64 rows (n)][32 k], all K-major SW128.
+constexpr int STG_OFF = 0;                          // 4 store tiles (2 column halves x hi/lo) of 16 KiB, SW128, in
+static_assert(4 * A_PLANE_BYTES <= T_STAGES * T_STAGE_BYTES, "epilogue smem");  // the drained pipeline buffers
 
 __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_constant__ W2Round rp) {
   extern __shared__ uint8_t smem_raw[];
@@ -106,6 +98,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
   const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
   const int n = pr.n;
   const int n_k = n / TKF;
+  const int steps_per_acc = (n / 8 + T_MAX_ACC - 1) / T_MAX_ACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -139,7 +132,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
         uint8_t* st = smem + s * T_STAGE_BYTES;
         tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
         tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
-        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T = B
+        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
         tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
         if (++s == T_STAGES) { s = 0; ph ^= 1; }
       }
@@ -148,9 +141,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage.  The tensor core accumulates with
-    // truncation, so a long K chain drifts: hi*hi goes to a fresh TMEM accumulator every T_CHUNK stages and the
-    // small cross terms to their own; the epilogue adds them up in round-to-nearest fp32.
+    // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage.  The tensor core aligns every product to
+    // the accumulator and truncates, so a chain of m products loses ~2^-25 * m of the sum, systematically; on the
+    // ill-conditioned covariances of real activations the Newton-Schulz iteration turns that into a -1e-3 bias of the
+    // style terms (measured).  hi*hi therefore runs in short chains: the n/8 k-steps are dealt out in equal runs to
+    // six TMEM accumulators (2 steps each at C = 64 ... 11 at C = 512), the small cross terms go to a seventh, and
+    // the epilogue adds all of them in round-to-nearest fp32.
     constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
     constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
     const bool leader = elect_one();
@@ -166,10 +162,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
         const uint32_t b_l = umma_desc_lo(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
-          const uint32_t t_main = tmem_base + (k / T_CHUNK) * TN, t_cross = tmem_base + T_CROSS_COL;
-          umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, (k > 0) | (kk > 0));
+          const int step = k * (TKF / 8) + kk;
+          const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+          umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
           umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
-          umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, (k % T_CHUNK > 0) | (kk > 0));
+          umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
         }
         umma_commit(&empty[s]);
       }
@@ -184,16 +181,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
     const int r = wq * 32 + lane;
     const int gi = ti * TM + r;
     const size_t nn = (size_t)n * n;
-    const int cls = pr.sym ? min(tj - 2 * ti, 2) : 3;       // 0: "A", 1: "B", 2: strictly upper, 3: not symmetric
-    const int mb = cls == 0 ? 0 : (cls == 1 ? TN : -1);     // first row of the self-mirroring block, if any
-    const int store_rows = cls == 0 ? TN : TM;
-    float* S = reinterpret_cast<float*>(smem);
     uint8_t* stg = smem + STG_OFF;
     mbar_wait(t_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const int n_chunks = (n_k + T_CHUNK - 1) / T_CHUNK;
-    // pass 1: accumulators -> alpha, + gamma I -> raw tile in shared memory
+    const int n_chunks = (n / 8 + steps_per_acc - 1) / steps_per_acc;
+    const bool valid = gi < n;
+    float ssq = 0.f, tr = 0.f;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
@@ -211,58 +205,36 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
       tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
       tmem_ld_wait();
       const int gj0 = tj * TN + h * 32;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float o = (acc[e] + __uint_as_float(v[e])) * pr.alpha;
-        if (gi == gj0 + e) o += pr.gamma;
-        S[r * S_PITCH + h * 32 + e] = o;
-      }
-    }
-    tc_fence_before();
-    named_bar_sync(1, 128);
-    // pass 2: symmetrise the diagonal block, split, stage for the TMA store, mirror
-    const bool in_block = mb >= 0 && r >= mb && r < mb + TN;
-    const int rl = r - mb;
-    const bool stored = r < store_rows && gi < n;
-    const bool mirrored = gi < n && (cls == 2 || (cls == 1 && r < TN));
-    float ssq = 0.f, tr = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
       uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
       uint8_t* row_lo = row_hi + A_PLANE_BYTES;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = h * 32 + 4 * q + e;
-          o[e] = (in_block && c < rl) ? S[(mb + c) * S_PITCH + rl] : S[r * S_PITCH + c];
-          if (stored) {
-            ssq = fmaf(o[e], o[e], ssq);
-            if (gi == tj * TN + c) tr += o[e];
-          }
-        }
         float vh[4], vl[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(o[e], vh[e], vl[e]);
+        for (int e = 0; e < 4; ++e) {
+          float o = (acc[4 * q + e] + __uint_as_float(v[4 * q + e])) * pr.alpha;
+          if (gi == gj0 + 4 * q + e) { o += pr.gamma; tr += o; }
+          if (valid) ssq = fmaf(o, o, ssq);
+          split_tf32(o, vh[e], vl[e]);
+        }
         const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
         *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
         *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
-        if (mirrored) {  // (j,i) <- (i,j): for a fixed column the 32 lanes (consecutive rows) write 128 contiguous bytes
+        if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 B
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const size_t at = (size_t)(tj * TN + h * 32 + 4 * q + e) * n + gi;
+            const size_t at = 2 * nn + (size_t)(gj0 + 4 * q + e) * n + gi;
             pr.D[at] = vh[e];
             pr.D[nn + at] = vl[e];
-            ssq = fmaf(o[e], o[e], ssq);
           }
         }
       }
     }
+    tc_fence_before();
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (r == 0) {
-      const CUtensorMap* dm = pr.dmap + (store_rows == TN ? 2 : 0);
+      const CUtensorMap* dm = pr.dmap;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
@@ -303,14 +275,7 @@ __device__ __forceinline__ void sum_partials(const float* red, int count, float&
   a = 0.f; b = 0.f;
   for (int i = 0; i < count; ++i) { a += red[2 * i]; b += red[2 * i + 1]; }
 }
-// partials of a symmetric GEMM result: only the tiles that touch the upper triangle were scheduled
-__device__ __forceinline__ void sum_partials_sym(const float* red, int n, float& a, float& b) {
-  a = 0.f; b = 0.f;
-  const int ntj = n / TN;
-  for (int ti = 0; ti < (n + TM - 1) / TM; ++ti)
-    for (int tj = 0; tj < ntj; ++tj)
-      if (tile_in_upper(ti, tj)) { a += red[(ti * ntj + tj) * 2]; b += red[(ti * ntj + tj) * 2 + 1]; }
-}
+__device__ __forceinline__ int gemm_tiles(int n) { return ((n + TM - 1) / TM) * (n / TN); }
 
 // covariance from (reduced) raw sums:  mu = sums/N; cov = S_raw/N - mu mu^T + eps I     (ST:171-173, 177)
 // target mode: cov_t from (mean_t, srm_t), plus sum-of-squares partials of cov_t for the NS normalisation.
@@ -330,6 +295,7 @@ __global__ void __launch_bounds__(256) w2_cov_kernel(const W2Layer* __restrict__
     float v = S[(size_t)lo * n + hi] * inv_n - (sm[lo] * inv_n) * (sm[hi] * inv_n);
     if (i == j) v += L.eps;
     store_split(cov, nn, e, v);
+    store_split(cov + 2 * nn, nn, e, v);  // cov^T = cov bit-for-bit (upper triangle of S read for both)
     ssq = fmaf(v, v, ssq);
   }
   ssq = block_sum_256(ssq, s_red);
@@ -361,14 +327,14 @@ __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restri
   const size_t nn = (size_t)n * n;
   const float* M = from_target ? L.cov_t : L.M;
   float ss, dummy;
-  if (from_target) sum_partials(L.red, NB, ss, dummy);
-  else sum_partials_sym(L.red, n, ss, dummy);
+  sum_partials(L.red, from_target ? NB : gemm_tiles(n), ss, dummy);
   const float norm = sqrtf(ss);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
     store_split(L.Y[0], nn, e, load2(M, nn, e) / norm);
-    L.Z[0][e] = (i == j) ? 1.f : 0.f;
-    L.Z[0][nn + e] = 0.f;
+    store_split(L.Y[0] + 2 * nn, nn, e, load2(M, nn, (size_t)j * n + i) / norm);  // Y^T
+    const float z0 = (i == j) ? 1.f : 0.f;
+    L.Z[0][e] = z0; L.Z[0][nn + e] = 0.f; L.Z[0][2 * nn + e] = z0; L.Z[0][3 * nn + e] = 0.f;
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
 }
@@ -379,8 +345,10 @@ __global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   const float s = sqrtf(L.scal[W2S_NORM_A]);
-  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256)
+  for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     store_split(L.P, nn, e, load2(L.Y[0], nn, e) * s);
+    store_split(L.P + 2 * nn, nn, e, load2(L.Y[0] + 2 * nn, nn, e) * s);  // P^T from the planes of Y^T
+  }
 }
 
 // forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41).
@@ -390,7 +358,7 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   float ss, tr;
-  sum_partials_sym(L.red, n, ss, tr);
+  sum_partials(L.red, gemm_tiles(n), ss, tr);
   const float sq = sqrtf(L.scal[W2S_NORM_A]);
   const float norm_y = sqrtf(ss);
   const float norm_r = sq * norm_y;                     // ||R||_F
@@ -399,7 +367,10 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
     store_split(L.A[0], nn, e, load2(L.Y[0], nn, e) / norm_y);   // a = z / ||z||
-    store_split(L.Q[0], nn, e, (i == j) ? seed : 0.f);
+    store_split(L.A[0] + 2 * nn, nn, e, load2(L.Y[0] + 2 * nn, nn, e) / norm_y);
+    const float q0 = (i == j) ? seed : 0.f;
+    store_split(L.Q[0], nn, e, q0);
+    store_split(L.Q[0] + 2 * nn, nn, e, q0);
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) {
     const float cov_diff = (L.scal[W2S_TR_COV_T] + L.scal[W2S_TR_COV] - 2.f * tr_r) / n;
@@ -451,8 +422,8 @@ int W2Engine::read_matrix(float* dst, const float* pair, int n, cudaStream_t s) 
 
 // ================================================================================================ host engine
 size_t W2Engine::layer_floats(int n) {
-  // plane pairs (hi, lo): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
-  return (size_t)(17 * 2 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
+  // 4 planes (hi, lo, hi^T, lo^T): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
+  return (size_t)(17 * 4 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
 }
 
 size_t W2Engine::workspace_bytes() {
@@ -476,35 +447,37 @@ struct Builder {
     const int idx = (int)maps.size();
     maps.resize(idx + 4);
     const size_t nn = (size_t)n * n;
-    int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);           // 128-row boxes: A loads, D stores
+    int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);               // 128-row boxes: A loads, D stores
     if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m, n, n, TKF, TN);       // 64-row boxes: B loads (B symmetric),
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + nn, n, n, TKF, TN);  // D stores of diagonal half tiles
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m + 2 * nn, n, n, TKF, TN);  // 64-row boxes on the planes of the
+    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + 3 * nn, n, n, TKF, TN);  // transpose: B loads
     if (r) rc = r;
     map_index[m] = idx;
     return idx;
   }
   void begin_round() { rounds->emplace_back(); rounds->back().n_tiles = 0; rounds->back().n_probs = 0; }
-  // D = alpha A B + gamma I with B symmetric; sym: D is symmetric too (upper tiles + mirrored stores)
+  // D = alpha op(A) B' + gamma I.  a_t: op(A) = A^T (its planes sit 2*n*n floats after A's).  b_t: B' = B^T, whose
+  // K-major rows are B's own planes 0,1 -- registered under the key B - 2*n*n so that "+2" lands on them.
+  // write_t: also emit the planes of D^T (D is later used as a right factor).
   void add(int n, float* D, const float* A, const float* B, float alpha, float gamma = 0.f, float* red_out = nullptr,
-           int sym = 1) {
+           int write_t = 1, int a_t = 0, int b_t = 0) {
     W2Round& R = rounds->back();
     if (R.n_probs >= W2_MAX_PROBS) { rc = STB_ERR_STATE; return; }
+    const size_t nn = (size_t)n * n;
     TcProb& p = R.probs[R.n_probs];
-    p.amap = d_maps + maps_for(A, n);
-    p.bmap = d_maps + maps_for(B, n) + 2;
+    p.amap = d_maps + maps_for(a_t ? A + 2 * nn : A, n);
+    p.bmap = d_maps + maps_for(b_t ? B - 2 * nn : B, n) + 2;
     p.dmap = d_maps + maps_for(D, n);
-    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.sym = sym;
+    p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.write_t = write_t;
     for (int i = 0; i < (n + TM - 1) / TM; ++i)
-      for (int j = 0; j < n / TN; ++j)
-        if (!sym || tile_in_upper(i, j)) {
-          if (R.n_tiles >= W2_MAX_TILES) { rc = STB_ERR_STATE; return; }
-          R.tiles[R.n_tiles++] = (uint32_t)R.n_probs << 16 | (uint32_t)i << 8 | (uint32_t)j;
-        }
+      for (int j = 0; j < n / TN; ++j) {
+        if (R.n_tiles >= W2_MAX_TILES) { rc = STB_ERR_STATE; return; }
+        R.tiles[R.n_tiles++] = (uint32_t)R.n_probs << 16 | (uint32_t)i << 8 | (uint32_t)j;
+      }
     ++R.n_probs;
   }
 };
-constexpr int MAX_MAPS = 5 * 24 * 4;
+constexpr int MAX_MAPS = 5 * 28 * 4;
 }  // namespace
 
 int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
@@ -515,7 +488,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int l = 0; l < 5; ++l) {
     W2Layer& L = host_layers[l];
     const int n = n_per_layer[l];
-    const size_t nn = (size_t)n * n * 4, pp = 2 * nn;  // single plane / (hi, lo) pair
+    const size_t nn = (size_t)n * n * 4, pp = 4 * nn;  // single plane / (hi, lo, hi^T, lo^T)
     L.n = n;
     L.eps = 1e-4f;
     L.cov = (float*)take(pp); L.M = (float*)take(pp); L.X = (float*)take(pp);
@@ -545,10 +518,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     for (int it = 0; it < 12; ++it) {
       const int s = it & 1, d = s ^ 1;
       begin_round();
-      for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.T, L.Z[s], L.Y[s], -0.5f, 1.5f); }
+      for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.T, L.Z[s], L.Y[s], -0.5f, 1.5f); }
       end_round();
       begin_round();
-      for (int l = 0; l < 5; ++l) {
+      for (int l = 4; l >= 0; --l) {  // largest matrices first: the two CTAs beyond 148 are short ones
         W2Layer& L = host_layers[l];
         b.add(L.n, L.Y[d], L.Y[s], L.T, 1.f, 0.f, it == 11 ? L.red : nullptr);
         if (it < 11) b.add(L.n, L.Z[d], L.T, L.Z[s], 1.f);  // Z is dead after the last Y
@@ -563,10 +536,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   // (b) iterate forward: X = P cov; M = X P; NS
   r_fwd_begin = (int)rounds.size();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }  // not symmetric
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }
   end_round();
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red); }
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red, 0); }
   end_round();
   r_fwd_ns_begin = (int)rounds.size();
   ns_rounds();
@@ -579,24 +552,23 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int it = 0; it < 12; ++it) {
     const int s = it & 1, d = s ^ 1;
     begin_round();
-    for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.E, L.A[s], L.A[s], -1.f, 3.f); }
+    for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.E, L.A[s], L.A[s], -1.f, 3.f); }
     end_round();
     begin_round();
-    for (int l = 0; l < 5; ++l) {
+    for (int l = 4; l >= 0; --l) {
       W2Layer& L = host_layers[l];
       b.add(L.n, L.Q[d], L.Q[s], L.E, 0.5f);
       if (it < 11) b.add(L.n, L.A[d], L.A[s], L.E, 0.5f);
     }
     end_round();
   }
-  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I with P^T = P bit-for-bit (gamma patched per
-  // layer in upload_layers).  U is not symmetric; Gc is, but its consumer forms Gc + Gc^T from all of it.
+  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I   (gamma patched per layer in upload_layers)
   begin_round();
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0); }
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0, 1, 0); }
   end_round();
   begin_round();
   gc_round = (int)rounds.size() - 1;
-  for (int l = 0; l < 5; ++l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f, nullptr, 0); }
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.Gc, L.U, L.P, 0.5f, 0.f, nullptr, 0, 0, 1); }
   end_round();
   r_bwd_end = (int)rounds.size();
   STB_CHECK(b.rc == 0, STB_ERR_CUDA, "W2 round construction failed (%d): %s", b.rc, last_error_string().c_str());
@@ -610,7 +582,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
 
 int W2Engine::upload_layers(cudaStream_t s) {
   // layer weights enter the Gc round through gamma = w / C (rounds travel as kernel parameters)
-  for (int l = 0; l < 5; ++l) rounds[gc_round].probs[l].gamma = host_layers[l].weight / host_layers[l].n;
+  for (int l = 0; l < 5; ++l) rounds[gc_round].probs[4 - l].gamma = host_layers[l].weight / host_layers[l].n;
   STB_CUDA_CHECK(cudaMemcpyAsync(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice, s));
   return STB_OK;
 }

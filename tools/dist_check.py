@@ -44,7 +44,7 @@ tr_b, img_b, t_b = run(True)
 tr_s, img_s, t_s = run(False)
 rel = np.abs(tr_b - tr_s) / np.abs(tr_s)
 d = np.abs(img_b - img_s)
-ok = rel.max() < 2e-4 and d.mean() < 0.5
+ok = rel.max() < 5e-4 and d.mean() < 0.5  # 1e-3 is the loss bar; summation order alone moves the loss by ~1e-4
 print(f'[rank {rank}/{world}] banded {tr_b[:3]}..{tr_b[-1]:.6f} ({t_b:.2f}s) single {tr_s[:3]}..{tr_s[-1]:.6f} ({t_s:.2f}s) '
       f'max rel loss diff {rel.max():.2e}  image mean |diff| {d.mean():.3f}/255 max {d.max():.0f}  {"OK" if ok else "BAD"}',
       flush=True)

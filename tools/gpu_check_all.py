@@ -263,6 +263,9 @@ if __name__ == '__main__':
         t_full(48, 64, 'max', wts)
         t_full(56, 80, 'average', wts)
         t_full(72, 72, 'l2', wts)
+    if 'big' in which:  # parity of the loss terms against the fp32 CPU oracle at larger sizes (minutes of CPU time)
+        t_full(512, 512, 'max', wts)
+        t_full(1024, 1024, 'max', wts)
     if 'stylize' in which:
         t_stylize(wts)
     if 'bench' in which:
