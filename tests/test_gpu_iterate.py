@@ -64,6 +64,34 @@ def test_targets_loss_and_gradient(G, vgg_weights, H, W, pooling):
         assert cos > tol_cos
 
 
+def test_loss_parity_at_512(G, vgg_weights):
+    """The loss bar must hold where the accumulation chains are long: at 512^2 every style term's Gram runs over
+    262 144 pixels and the ill-conditioned (eps = 1e-4) covariances amplify any bias of the tensor-core accumulation
+    (a mirrored / long-chain W2 engine was -1.3e-3 here while passing every small case)."""
+    H = W = 512
+    st = G.make_st('max', vgg_weights)
+    cimg = O.to_tensor(O.synth_image(1, 16, W, H))
+    simg = O.to_tensor(O.synth_image(2, 32, W - 8, H - 4))
+    m = st.model
+    m.ensure_workspace([(H, W), tuple(simg.shape[2:])])
+    ct = m.content_features(cimg.to(G.DEV))
+    means, srms = m.style_stats(simg.to(G.DEV))
+    m.set_targets(H, W, ct, 0.015, means, srms, st.style_weights, 2.0)
+    torch.manual_seed(0)
+    img = (cimg + 0.05 * torch.randn_like(cimg)).clamp(0, 1)
+    st.image = img.to(G.DEV).contiguous()
+    terms, _ = st.loss_and_grad()
+    a_s = O.vgg_forward(simg, vgg_weights, 'max', 29)
+    a_c = O.vgg_forward(cimg, vgg_weights, 'max', 22)
+    tg = O.ScaleTargets(a_c[22], [O.StyleTarget.build(*O.style_stats(a_s[layer])) for layer in O.STYLE_LAYERS],
+                        0.015, 2.0)
+    det = {}
+    ol, _ = O.loss_and_grad(img, vgg_weights, tg, 'max', detail=det)
+    assert abs(terms[0].item() - float(ol)) / float(ol) < 1e-3   # north_star bar; measured 1.5e-4
+    # the two large style terms (relu1_1, relu2_1 = 2/3 of the loss) individually
+    np.testing.assert_allclose(terms[2:4].numpy(), det['terms'][1:3], rtol=1e-3)
+
+
 @pytest.mark.parametrize('name', ['max_64x48_single', 'avg_80x56_two_styles', 'l2_72x72_single', 'max_pyramid_32_64',
                                   'max_128_noise_tv'])
 def test_stylize_matches_reference_golden(G, vgg_weights, name):
