@@ -17,6 +17,7 @@ from pathlib import Path
 import torch
 from PIL import Image
 
+from .image_io import AsyncImageWriter
 from .style_transfer import StyleTransfer
 
 _SHORT = {'content_weight': 'cw', 'tv_weight': 'tw', 'optimizer': None, 'min_scale': 'ms', 'end_scale': 's',
@@ -90,19 +91,21 @@ def main(argv=None):
     torch.manual_seed(args.random_seed)
     st = StyleTransfer(devices=[str(d) for d in devices], pooling=args.pooling)
     trace = []
+    writer = AsyncImageWriter()  # periodic saves are encoded off the loop's critical path (image_io.py)
 
     def on_iterate(it):
         trace.append(asdict(it))
         print(f'Size: {it.w}x{it.h}, iteration: {it.i}, loss: {it.loss:g}')
         last_of_scale = it.i == it.i_max
         if (args.save_every and it.i % args.save_every == 0) or (last_of_scale and max(it.w, it.h) != args.end_scale):
-            st.get_image().save(out_path)
+            writer.submit_snapshot(st, out_path)
 
     kwargs = {k: getattr(args, k) for k in _SHORT}
     try:
         st.stylize(content, styles, style_weights=args.style_weights, callback=on_iterate, **kwargs)
     except KeyboardInterrupt:
         pass
+    writer.close()
     image = st.get_image()
     if image is not None:
         print(f'Writing image to {out_path}.')

@@ -447,14 +447,16 @@ class StyleTransfer:
                     else:
                         loss_value = self._lbfgs_step(lbfgs, avg_decay)
                     if callback is not None:
-                        if optimizer == 'adam':
-                            torch.cuda.current_stream().synchronize()
-                            self.last_loss_terms = self._loss_host.clone()
-                            loss_value = float(self._loss_host[0])
+                        # host-side bookkeeping first: it overlaps the iteration still running on the device (the
+                        # native path allocates nothing, so the high-water mark cannot move before the sync)
                         gpu_ram = 0
                         for device in self.devices:
                             if device.type == 'cuda':
                                 gpu_ram = max(gpu_ram, torch.cuda.max_memory_allocated(device))
+                        if optimizer == 'adam':
+                            torch.cuda.current_stream().synchronize()   # the reference syncs here too (loss.item())
+                            self.last_loss_terms = self._loss_host.clone()
+                            loss_value = float(self._loss_host[0])
                         callback(STIterate(w=cw, h=ch, i=i, i_max=actual_its, loss=loss_value, time=time.time(),
                                            gpu_ram=gpu_ram))
 

@@ -177,3 +177,20 @@ def test_oracle_pool_variants_match_torch_modules():
         np.testing.assert_allclose(O.pool_fwd(x, name).numpy(), y.detach().numpy(), rtol=1e-5, atol=1e-6)
         ref = torch.nan_to_num(xr.grad, nan=0.0)
         np.testing.assert_allclose(O.pool_bwd(g, x, name).numpy(), ref.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_async_image_writer_saves_newest_snapshot(tmp_path):
+    """periodic saves go through a worker thread; newest snapshot wins, files are whole."""
+    import numpy as np
+    from PIL import Image
+    from style_transfer_b200 import image_io
+    w = image_io.AsyncImageWriter()
+    out = tmp_path / 'out.png'
+    for k in range(5):
+        w.submit_array(np.full((32, 48, 3), 40 * k, dtype=np.uint8), out)
+    other = tmp_path / 'other.png'
+    w.submit_array(np.zeros((8, 8, 3), dtype=np.uint8), other)
+    w.close()
+    img = np.asarray(Image.open(out))
+    assert img.shape == (32, 48, 3) and int(img[0, 0, 0]) == 160
+    assert other.exists() and not list(tmp_path.glob('*.part*'))

@@ -150,7 +150,7 @@ def make_st(pooling, wts):
     return stb.StyleTransfer(devices=['cuda:0'], pooling=pooling, vgg_weights=wts)
 
 
-def t_full(H, W, pooling, wts):
+def t_full(H, W, pooling, wts, sims=(False, True)):
     st = make_st(pooling, wts)
     content = O.synth_image(1, 16, W, H)
     style = O.synth_image(2, 32, W - 8, H - 4)
@@ -177,7 +177,7 @@ def t_full(H, W, pooling, wts):
     # oracle with the oracle's own targets (fp32) and with bf16 storage model
     style_t = [O.StyleTarget.build(*O.style_stats(acts_s[layer])) for layer in O.STYLE_LAYERS]
     tg = O.ScaleTargets(acts_c[22], style_t, 0.015, 2.0)
-    for sim in (False, True):
+    for sim in sims:
         if sim:
             a_s = O.vgg_forward(simg, wts, pooling, 29, True)
             a_c = O.vgg_forward(cimg, wts, pooling, 22, True)
@@ -266,6 +266,8 @@ if __name__ == '__main__':
     if 'big' in which:  # parity of the loss terms against the fp32 CPU oracle at larger sizes (minutes of CPU time)
         t_full(512, 512, 'max', wts)
         t_full(1024, 1024, 'max', wts)
+    if 'huge' in which:  # the BASELINE.json size itself against the fp32 oracle (about two minutes of host time)
+        t_full(2048, 2048, 'max', wts, sims=(False,))
     if 'stylize' in which:
         t_stylize(wts)
     if 'bench' in which:
