@@ -40,8 +40,8 @@ namespace {
 
 constexpr int TM = 128, TN = 64, TKF = 32;      // tile rows / cols, k floats per stage (128 B swizzle row)
 constexpr int T_STAGES = 4;
-constexpr int T_MAX_ACC = 6;                       // hi*hi accumulators: the K8 steps are dealt out to them in runs
-constexpr int T_TMEM_COLS = 512;                   // 6 x 64 hi*hi accumulators + 64 for the cross terms
+constexpr int T_MAX_ACC = 7;                       // hi*hi accumulators: the K8 steps are dealt out to them in runs
+constexpr int T_TMEM_COLS = 512;                   // 7 x 64 hi*hi accumulators + 64 for the cross terms
 constexpr int T_CROSS_COL = T_MAX_ACC * TN;
 constexpr int A_PLANE_BYTES = TM * 128;          // 16 KiB
 constexpr int B_PLANE_BYTES = TN * 128;          // 8 KiB
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
     // the accumulator and truncates, so a chain of m products loses ~2^-25 * m of the sum, systematically; on the
     // ill-conditioned covariances of real activations the Newton-Schulz iteration turns that into a -1e-3 bias of the
     // style terms (measured).  hi*hi therefore runs in short chains: the n/8 k-steps are dealt out in equal runs to
-    // six TMEM accumulators (2 steps each at C = 64 ... 11 at C = 512), the small cross terms go to a seventh, and
+    // seven TMEM accumulators (2 steps each at C = 64 ... 10 at C = 512), the small cross terms go to an eighth, and
     // the epilogue adds all of them in round-to-nearest fp32.
     constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
     constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
