@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restri
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
     store_split(L.Y[0], nn, e, load2(M, nn, e) / norm);
-    store_split(L.Y[0] + 2 * nn, nn, e, load2(M, nn, (size_t)j * n + i) / norm);  // Y^T
+    store_split(L.Y[0] + 2 * nn, nn, e, load2(M + 2 * nn, nn, e) / norm);  // Y^T from the planes of M^T (cov_t: symmetric)
     const float z0 = (i == j) ? 1.f : 0.f;
     L.Z[0][e] = z0; L.Z[0][nn + e] = 0.f; L.Z[0][2 * nn + e] = z0; L.Z[0][3 * nn + e] = 0.f;
   }
@@ -539,7 +539,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.X, L.P, L.cov, 1.f, 0.f, nullptr, 0); }
   end_round();
   begin_round();
-  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red, 0); }
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.M, L.X, L.P, 1.f, 0.f, L.red, 1); }  // M^T planes: ns_init reads them coalesced
   end_round();
   r_fwd_ns_begin = (int)rounds.size();
   ns_rounds();
