@@ -35,6 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 CONV_FLOP_PER_PIXEL = 1444608.0  # fwd + dgrad, 2 flop/MAC
+CONV0_FLOP_PER_PIXEL = 4 * 27 * 64.0  # conv0 fwd + dgrad run in their own kernels (conv0_tc.cu), not in the timed class
 PROF_CLASSES = ['conv0_fwd_tv', 'conv_fwd', 'pool_fwd', 'gram', 'sse', 'w2', 'conv_bwd', 'pool_bwd',
                 'conv0_bwd_adam', 'finalize']
 
@@ -298,7 +299,9 @@ def run_native(args, rank, local_rank, world):
 
     if rank == 0:
         peaks = measured_peaks()
-        conv_flops = CONV_FLOP_PER_PIXEL * h_loc * size  # this rank's rows (band + aprons when tiled)
+        # the twelve 3x3 convs of pixel_gemm_kernel on this rank's rows (band + aprons when tiled); the tap-gradient
+        # GEMMs folded into the same launches (0.15 TFLOP at 2048^2) are NOT credited
+        conv_flops = (CONV_FLOP_PER_PIXEL - CONV0_FLOP_PER_PIXEL) * h_loc * size
         conv_ms = prof['conv_fwd']['ms_per_iter'] + prof['conv_bwd']['ms_per_iter']
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks['bf16_tflops_sustained']
@@ -309,10 +312,10 @@ def run_native(args, rank, local_rank, world):
             traffic = json.loads(tpath.read_text())['dram_total_bytes']  # dram read+write of the conv launches, ncu
         roofline = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
                         traffic=traffic, peak_source=f"{peaks['source']} (bf16_tflops_sustained)",
-                        kernel='pixel_gemm_kernel (tcgen05 conv fwd+dgrad, 25 launches/iter)',
-                        note='algorithmic conv FLOPs/iter (1444608/pixel) / summed CUDA-event duration of the conv '
+                        kernel='pixel_gemm_kernel (tcgen05 conv fwd+dgrad incl. tap-gradient GEMMs, 25 launches/iter)',
+                        note='algorithmic FLOPs/iter of the twelve 3x3 convs (1437696/pixel) / summed CUDA-event duration of the conv '
                              'launches in an instrumented pass; traffic = DRAM bytes (read+write) of the same launches per '
-                             'iteration from one ncu --set full capture (profiles/r1_ncu_conv_summary.csv)',
+                             'iteration from one ncu --set full capture (profiles/r1_ncu_conv_v11.csv; algorithmic ~8.5 GB)',
                         step_fraction=conv_ms / sum(v['ms_per_iter'] for v in prof.values()),
                         classes_ms_per_iter={k: round(v['ms_per_iter'], 4) for k, v in prof.items()},
                         whole_step_tensor_frac=CONV_FLOP_PER_PIXEL * size * size * (1000.0 / ms_per_step) / 1e12 /
