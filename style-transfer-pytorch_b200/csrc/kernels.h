@@ -109,7 +109,7 @@ struct W2Layer {
   float* gmu_bias;  // out: (d loss / d mean) / npix              -> per-channel bias of the tap-gradient GEMM
   bf16* gs_bf16;    // out: (G + G^T) / npix as bf16 [n][n]       -> B operand of the tap-gradient GEMM
   float* scal;      // W2S_* scalars
-  float* red;       // reduction partials {sum of squares, trace} x 64
+  float* red;       // reduction partials {sum of squares, trace} x 128
 };
 struct W2Engine {
   W2Layer host_layers[5];

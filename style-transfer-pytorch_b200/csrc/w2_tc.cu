@@ -51,8 +51,9 @@ constexpr int T_OFF_TMEMPTR = T_OFF_BAR + (2 * T_STAGES + 1) * 8;
 constexpr int T_OFF_RED = T_OFF_TMEMPTR + 16;
 constexpr int T_SMEM_BYTES = T_OFF_RED + 64 + 1024;
 constexpr int T_THREADS = 64 + 128;
-constexpr int NRED = 64;   // max reduction partials per layer
-constexpr int NB = 32;     // helper-kernel CTAs per layer
+constexpr int NRED = 128;  // max reduction partials per layer
+constexpr int NB = 128;    // helper-kernel CTAs per layer: they are latency-bound element-wise passes (32 CTAs: 48 us)
+static_assert(NB <= NRED, "the covariance kernel writes one partial per CTA");
 
 // x = hi + lo with both parts rounded to nearest TF32 (the tensor core would otherwise truncate them: a biased
 // error that the loss' cancellation amplifies); x - hi is exact in fp32.
