@@ -305,7 +305,10 @@ def run_native(args, rank, local_rank, world):
         conv_ms = prof['conv_fwd']['ms_per_iter'] + prof['conv_bwd']['ms_per_iter']
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks['bf16_tflops_sustained']
-        launches = sum(v['launches_per_iter'] for v in prof.values())
+        # kernels per iteration: counted from the ncu launch list of one eager iteration
+        # (profiles/r1_launches_2048_v11.csv: 24 conv + 52 W2 rounds + 5 W2 helpers + 5 Gram + 5 reduce + conv0 fwd/bwd
+        # + border + TV + 4 pool bwd + SSE + 3 scalar/finalize kernels = 104); the tiled path adds adam_rows
+        launches = 104 + (1 if tiled else 0)
         traffic = None
         tpath = ROOT / 'profiles' / 'r1_conv_traffic.json'
         if tpath.exists() and size == 2048 and world == 1:
@@ -321,7 +324,7 @@ def run_native(args, rank, local_rank, world):
                         whole_step_tensor_frac=CONV_FLOP_PER_PIXEL * size * size * (1000.0 / ms_per_step) / 1e12 /
                         (peak * world))
         cb = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0, N = 1 only
             cb = cpu_baseline(size)
         line = dict(metric='stylize iterations/sec at end_scale=2048', value=value, unit='it/s', n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
