@@ -125,8 +125,13 @@ STB_API int stb_test_conv0_fwd(const float* img, const float* w0, const float* b
                                float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream);
 STB_API int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
                                void* stream);
-STB_API int stb_test_pool(int pooling, int backward, const void* in_or_gout, const void* y, void* out, int H, int W,
-                          int C, void* stream);
+/* conv 3x3 + bias + ReLU with the 2x2 pool fused into its epilogue (the product's only pool-forward path):
+ * out [H][W][Cout] and pool_out [H/2][W/2][Cout], both bf16 NHWC. */
+STB_API int stb_test_conv_pool(int H, int W, int Cin, int Cout, const void* A, const void* Bw, const float* bias,
+                               void* out, void* pool_out, int pooling, void* stream);
+/* pool backward (+ ReLU mask of the pool input y): gin [H][W][C] from gout [H/2][W/2][C]. */
+STB_API int stb_test_pool_bwd(int pooling, const void* gout, const void* y, void* gin, int H, int W, int C,
+                              void* stream);
 STB_API int stb_test_gram(const void* F_bf16, long P, int C, float* partials_ws, size_t partials_floats,
                           float* S_raw, float* sums, void* stream);
 STB_API size_t stb_test_gram_partials_floats(long P, int C);

@@ -43,7 +43,8 @@ def _declare(lib):
         'stb_test_pixel_gemm': [i, i, i, i, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, f, i, i, vp],
         'stb_test_conv0_fwd': [vp, vp, vp, vp, i, i, f, vp, vp, C.POINTER(i), vp],
         'stb_test_conv0_bwd': [vp, vp, vp, vp, i, i, vp],
-        'stb_test_pool': [i, i, vp, vp, vp, i, i, i, vp],
+        'stb_test_conv_pool': [i, i, i, i, vp, vp, vp, vp, vp, i, vp],
+        'stb_test_pool_bwd': [i, vp, vp, vp, i, i, i, vp],
         'stb_test_gram': [vp, C.c_long, i, vp, sz, vp, vp, vp],
         'stb_test_w2': [vp, vp, vp, vp, i, f, f, vp, sz, vp, vp, vp, vp, vp],
     }
@@ -64,7 +65,7 @@ EXPORTS = [
     'stb_style_stats', 'stb_content_features', 'stb_set_targets', 'stb_iterate', 'stb_iterate_ex',
     'stb_set_band', 'stb_stats_block', 'stb_iterate_fwd', 'stb_iterate_bwd', 'stb_adam_update',
     'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation', 'stb_pack_weights', 'stb_test_pixel_gemm', 'stb_test_conv0_fwd', 'stb_test_conv0_bwd',
-    'stb_test_pool', 'stb_test_gram', 'stb_test_gram_partials_floats', 'stb_test_w2', 'stb_test_w2_workspace_bytes',
+    'stb_test_conv_pool', 'stb_test_pool_bwd', 'stb_test_gram', 'stb_test_gram_partials_floats', 'stb_test_w2', 'stb_test_w2_workspace_bytes',
 ]
 
 

@@ -71,12 +71,22 @@ int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, f
   return rc;
 }
 
-int stb_test_pool(int pooling, int backward, const void* in_or_gout, const void* y, void* out, int H, int W, int C,
-                  void* stream) {
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!backward) return launch_pool_fwd(pooling, static_cast<const bf16*>(in_or_gout), static_cast<bf16*>(out), H, W, C, s);
-  return launch_pool_bwd(pooling, static_cast<const bf16*>(in_or_gout), static_cast<const bf16*>(y),
-                         static_cast<bf16*>(out), H, W, C, s);
+int stb_test_conv_pool(int H, int W, int Cin, int Cout, const void* A, const void* Bw, const float* bias, void* out,
+                       void* pool_out, int pooling, void* stream) {
+  PixelGemmArgs a;
+  a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.mode = 0;
+  a.A = static_cast<const bf16*>(A);
+  a.Bw = static_cast<const bf16*>(Bw);
+  a.out = static_cast<bf16*>(out);
+  a.bias = bias;
+  a.pool_out = static_cast<bf16*>(pool_out);
+  a.pooling = pooling;
+  return launch_pixel_gemm(a, static_cast<cudaStream_t>(stream));
+}
+
+int stb_test_pool_bwd(int pooling, const void* gout, const void* y, void* gin, int H, int W, int C, void* stream) {
+  return launch_pool_bwd(pooling, static_cast<const bf16*>(gout), static_cast<const bf16*>(y), static_cast<bf16*>(gin),
+                         H, W, C, static_cast<cudaStream_t>(stream));
 }
 
 size_t stb_test_gram_partials_floats(long P, int C) { return gram_partials_floats(P, C); }

@@ -263,49 +263,7 @@ conv0_bwd_adam_kernel(const bf16* __restrict__ g0, const bool interior_done, con
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
-// one thread = one output pixel x 8 channels (16 B); NHWC bf16.
-template <int POOL>
-__global__ void __launch_bounds__(256)
-pool_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W, int C) {
-  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
-  const long total = (long)Ho * Wo * C8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = i % C8;
-    const long p = i / C8;
-    const int xo = p % Wo, yo = p / Wo;
-    const bf16* base = in + ((size_t)(2 * yo) * W + 2 * xo) * C + c8 * 8;
-    uint4 v[4];
-    v[0] = __ldg(reinterpret_cast<const uint4*>(base));
-    v[1] = __ldg(reinterpret_cast<const uint4*>(base + C));
-    v[2] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C));
-    v[3] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * C + C));
-    uint32_t r[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float lo[4], hi[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t u = reinterpret_cast<const uint32_t*>(&v[q])[k];
-        lo[q] = bf16lo(u);
-        hi[q] = bf16hi(u);
-      }
-      float a, b;
-      if (POOL == STB_POOL_MAX) {
-        a = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
-        b = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
-      } else if (POOL == STB_POOL_AVERAGE) {
-        a = (lo[0] + lo[1] + lo[2] + lo[3]) * 0.25f * 2.0f;
-        b = (hi[0] + hi[1] + hi[2] + hi[3]) * 0.25f * 2.0f;
-      } else {
-        a = sqrtf(lo[0] * lo[0] + lo[1] * lo[1] + lo[2] * lo[2] + lo[3] * lo[3]) * 0.78f;
-        b = sqrtf(hi[0] * hi[0] + hi[1] * hi[1] + hi[2] * hi[2] + hi[3] * hi[3]) * 0.78f;
-      }
-      r[k] = pack_bf16x2(a, b);
-    }
-    *reinterpret_cast<uint4*>(out + ((size_t)yo * Wo + xo) * C + c8 * 8) = make_uint4(r[0], r[1], r[2], r[3]);
-  }
-}
-
+// (pool forward lives in the epilogue of the conv that feeds it: conv_tc.cu)
 // backward through pool + the ReLU that produced the pool input y:  gin = pool_bwd(gout; y) * (y > 0).
 // One thread = one 2x2 input window x 8 channels; windows beyond the floor-mode extent write zeros.
 template <int POOL>
@@ -452,17 +410,6 @@ static int grid_for(long work_items, int block) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
-}
-
-int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s) {
-  const long total = (long)(H / 2) * (W / 2) * (C / 8);
-  if (total == 0) return STB_OK;
-  const int g = grid_for(total, 256);
-  if (pooling == STB_POOL_MAX) pool_fwd_kernel<STB_POOL_MAX><<<g, 256, 0, s>>>(in, out, H, W, C);
-  else if (pooling == STB_POOL_AVERAGE) pool_fwd_kernel<STB_POOL_AVERAGE><<<g, 256, 0, s>>>(in, out, H, W, C);
-  else pool_fwd_kernel<STB_POOL_L2><<<g, 256, 0, s>>>(in, out, H, W, C);
-  STB_CUDA_CHECK(cudaGetLastError());
-  return STB_OK;
 }
 
 int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s) {

@@ -67,7 +67,6 @@ int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s);
 int launch_conv0_bwd_interior(const bf16* g0, const bf16* w0q, const float* gtv, float* img, float* exp_avg,
                               float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars* d_adam,
                               int apply_update, cudaStream_t s);
-int launch_pool_fwd(int pooling, const bf16* in, bf16* out, int H, int W, int C, cudaStream_t s);
 int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s);
 int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s);
 

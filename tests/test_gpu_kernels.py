@@ -129,29 +129,46 @@ def test_conv0_tv_forward_and_backward(G, H, W):
 
 @pytest.mark.parametrize('H,W,C', [(16, 16, 64), (37, 21, 128), (2, 2, 512)])
 @pytest.mark.parametrize('pooling', ['max', 'average', 'l2'])
-def test_pool_forward_backward(G, H, W, C, pooling):
+def test_pool_backward(G, H, W, C, pooling):
     code = {'max': 0, 'average': 1, 'l2': 2}[pooling]
     g = torch.Generator().manual_seed(5)
     x = torch.relu(torch.randn(H, W, C, generator=g)).bfloat16()
     x[::3, ::2] = 0  # all-zero windows and ties
     go = torch.randn(H // 2, W // 2, C, generator=g).bfloat16()
     x_d, go_d = x.to(G.DEV), go.to(G.DEV)
-    out = torch.empty(H // 2, W // 2, C, dtype=torch.bfloat16, device=G.DEV)
-    G.check(G.lib().stb_test_pool(code, 0, G.P(x_d), None, G.P(out), H, W, C, G.S()))
     gin = torch.full((H, W, C), float('nan'), dtype=torch.bfloat16, device=G.DEV)
-    G.check(G.lib().stb_test_pool(code, 1, G.P(go_d), G.P(x_d), G.P(gin), H, W, C, G.S()))
+    G.check(G.lib().stb_test_pool_bwd(code, G.P(go_d), G.P(x_d), G.P(gin), H, W, C, G.S()))
     torch.cuda.synchronize()
     xin = G.nchw(x)
-    ref = O.pool_fwd(xin, pooling)
-    if pooling == 'max':
-        assert torch.equal(G.nchw(out).cpu(), ref)  # selection is exact
-    else:
-        assert G.rel_err(G.nchw(out), ref) < 5e-3
     gref = O.pool_bwd(G.nchw(go), xin, pooling) * (xin > 0)
     if pooling == 'max':
         assert torch.equal(G.nchw(gin).cpu(), gref)  # argmax routing (first maximum wins) is exact
     else:
         assert G.rel_err(G.nchw(gin), gref) < 5e-3
+
+
+@pytest.mark.parametrize('H,W,Cin,Cout', [(32, 24, 64, 64), (37, 21, 64, 128), (18, 50, 128, 256), (6, 6, 512, 512)])
+@pytest.mark.parametrize('pooling', ['max', 'average', 'l2'])
+def test_conv_with_fused_pool(G, H, W, Cin, Cout, pooling):
+    """The product's pool forward is the conv epilogue: pooled output == pool(conv output as stored), floor mode."""
+    code = {'max': 0, 'average': 1, 'l2': 2}[pooling]
+    g = torch.Generator().manual_seed(H * W + Cout)
+    x = torch.randn(H, W, Cin, generator=g).bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    xd, wd, bd = x.to(G.DEV), w.to(G.DEV), b.to(G.DEV)
+    wp = G.pack(wd, False)
+    out = torch.full((H, W, Cout), float('nan'), dtype=torch.bfloat16, device=G.DEV)
+    pooled = torch.full((H // 2, W // 2, Cout), float('nan'), dtype=torch.bfloat16, device=G.DEV)
+    G.check(G.lib().stb_test_conv_pool(H, W, Cin, Cout, G.P(xd), G.P(wp), G.P(bd), G.P(out), G.P(pooled), code, G.S()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(G.nchw(x), w.bfloat16().float(), b, padding=1))
+    assert G.rel_err(G.nchw(out), ref) < 6e-3
+    pref = O.pool_fwd(G.nchw(out).cpu(), pooling)          # pool of the conv output exactly as stored (bf16)
+    if pooling == 'max':
+        assert torch.equal(G.nchw(pooled).cpu(), pref)     # selection is exact
+    else:
+        assert G.rel_err(G.nchw(pooled), pref) < 5e-3
 
 
 @pytest.mark.parametrize('P_,C', [(16, 512), (1000, 64), (4096, 128), (3001, 256), (5000, 512), (1, 64)])
