@@ -16,6 +16,8 @@
 //               Weights stream tap by tap through a second ring.
 //   warp 1      single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32), double-buffered accumulators.
 //   warps 2-5   epilogue: tcgen05.ld -> bias/ReLU or mask/content -> bf16 -> swizzled smem -> TMA store.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -92,7 +94,6 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_chunks2 = p.C2 >> 6;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < p.Cout && i < 512; i += NUM_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -110,6 +111,13 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch (see launch_cfg): everything above touched no global data and may have run while
+  // the previous kernel of the iteration was still draining; its outputs (activations, and in MODE 1 the bias = gmu
+  // produced by the W2 chain) are read only from here on.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int i = threadIdx.x; i < p.Cout && i < 512; i += NUM_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
 
   if (warp == 0) {
     // =============================================================== TMA producer
@@ -389,8 +397,20 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     attr_set = true;
   }
   int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp);
-  STB_CUDA_CHECK(cudaGetLastError());
+  // launched with programmatic stream serialization: the CTAs may become resident (and run their prologue) as soon
+  // as the previous kernel's CTAs retire; griddepcontrol.wait in the kernel orders the data accesses
+  static const bool pdl = [] { const char* e = getenv("STB_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, tmOut, tmPool, kp));
   return STB_OK;
 }
 
