@@ -138,19 +138,25 @@ def cpu_baseline(size, budget_s=25.0):
     from oracle import reference_harness as RH
     if RH.reference_available():
         kind, what = 'reference', 'unmodified reference StyleTransfer.stylize(devices=[cpu]), median of STIterate.time diffs'
-        t256, threads = cpu_reference_iteration_time(256, 3)
-        big = 512 if t256 * 4 * 6 < budget_s else 384
-        tbig, _ = cpu_reference_iteration_time(big, 3)
+        timer, its = cpu_reference_iteration_time, 3
     else:
-        kind, what = 'port', 'oracle port (torch-CPU explicit schedule), median of 2 its'
-        t256, threads = cpu_port_iteration_time(256, 2, 1)
-        big = 512 if t256 * 4 * 3 < budget_s else 384
-        tbig, _ = cpu_port_iteration_time(big, 2, 1)
-    b = (tbig - t256) / (big * big - 256 * 256)
-    a = max(t256 - b * 256 * 256, 0.0)
+        kind, what = 'port', 'oracle port (torch-CPU explicit schedule), median'
+        timer, its = (lambda size_, n: cpu_port_iteration_time(size_, n, 1)), 2
+    # two bounded samples; the larger one as close to the target size as the time budget allows (cache effects make
+    # the small sizes optimistic)
+    small = 256
+    t256, threads = timer(small, its)
+    big = 512
+    for cand in (1024, 768):
+        if t256 * (cand * cand) / (small * small) * (its + 3) < budget_s:
+            big = cand
+            break
+    tbig, _ = timer(big, its)
+    b = (tbig - t256) / (big * big - small * small)
+    a = max(t256 - b * small * small, 0.0)
     t_full = a + b * size * size
     return dict(value=1.0 / t_full, unit='it/s', cores=threads, kind=kind,
-                sample=f'{what}: 256^2 ({t256:.3f} s/it) and {big}^2 ({tbig:.3f} s/it), affine-in-pixels '
+                sample=f'{what}: {small}^2 ({t256:.3f} s/it) and {big}^2 ({tbig:.3f} s/it), affine-in-pixels '
                        f'extrapolation to {size}^2 ({t_full:.2f} s/it)')
 
 

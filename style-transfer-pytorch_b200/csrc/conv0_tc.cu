@@ -434,11 +434,7 @@ __global__ void pack_w0_bwd_q_kernel(const float* __restrict__ w0, bf16* __restr
 
 int launch_conv0_fwd(const float* img, const bf16* w0_packed, const float* bias, bf16* out, int H, int W,
                      cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA_CHECK(cudaFuncSetAttribute(conv0_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
-    attr_set = true;
-  }
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv0_fwd_kernel), C0_SMEM));
   CUtensorMap tm;
   STB_TRY(make_tmap_bf16_3d(&tm, out, 64, W, H, 128ull, (uint64_t)W * 128ull, 64, W < C0_PX ? W : C0_PX, 1));
   const int n_items = ((H + C0_ROWS - 1) / C0_ROWS) * ((W + C0_PX - 1) / C0_PX);
@@ -462,11 +458,7 @@ int launch_conv0_bwd_interior(const bf16* g0, const bf16* w0q, const float* gtv,
                               float* exp_avg_sq, float* ema, float* grad_out, int H, int W, const AdamScalars* d_adam,
                               int apply_update, cudaStream_t s) {
   if (H < 3 || W < 3) return STB_OK;  // no interior pixels
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA_CHECK(cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
-    attr_set = true;
-  }
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv0_bwd_kernel), BW_SMEM));
   CUtensorMap tm;
   STB_TRY(make_tmap_bf16_3d(&tm, g0, 64, W, H, 128ull, (uint64_t)W * 128ull, 64, C0_PX, 1));
   const int n_items = ((W + BW_OUT - 1) / BW_OUT) * ((H + BW_ROWS - 1) / BW_ROWS);

@@ -390,12 +390,8 @@ template <int BN, int MODE>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
                const CUtensorMap& tmOut, const CUtensorMap& tmPool, const KParams& kp, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
   auto kern = pixel_gemm_kernel<BN, MODE>;
-  if (!attr_set) {
-    STB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
   // launched with programmatic stream serialization: the CTAs may become resident (and run their prologue) as soon
   // as the previous kernel's CTAs retire; griddepcontrol.wait in the kernel orders the data accesses

@@ -259,12 +259,8 @@ gram_reduce_kernel(const float* __restrict__ part0, float* __restrict__ out0, lo
 template <int BN>
 int launch_gram_cfg(const CUtensorMap& tm, const GParams& gp, int n_tiles, int n_splits, cudaStream_t stream) {
   using C = GCfg<BN>;
-  static bool attr_set = false;
   auto kern = gram_kernel<BN>;
-  if (!attr_set) {
-    STB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   kern<<<dim3(n_tiles, n_splits), G_THREADS, C::SMEM_BYTES, stream>>>(tm, gp);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;

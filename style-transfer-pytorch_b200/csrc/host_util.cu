@@ -2,6 +2,8 @@
 
 #include <cstdarg>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace stb {
 
@@ -72,6 +74,19 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   STB_CHECK(r == CUDA_SUCCESS, STB_ERR_CUDA, "cuTensorMapEncodeTiled(f32 2d) failed (%d): %llux%llu box %ux%u", (int)r,
             (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+  return STB_OK;
+}
+
+int ensure_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;  // (kernel, device)
+  int dev = 0;
+  STB_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == func && d.second == dev) return STB_OK;
+  STB_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(func, dev);
   return STB_OK;
 }
 

@@ -46,4 +46,8 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
 
 int num_sms();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember it per (kernel, device) so that contexts
+// on several GPUs of one process all get it.
+int ensure_dynamic_smem(const void* func, int bytes);
+
 }  // namespace stb

@@ -589,11 +589,7 @@ int W2Engine::upload_layers(cudaStream_t s) {
 }
 
 int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA_CHECK(cudaFuncSetAttribute(w2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES));
-    attr_set = true;
-  }
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(w2_gemm_kernel), T_SMEM_BYTES));
   static const bool pdl = [] { const char* e = getenv("STB_PDL"); return !(e && e[0] == '0'); }();
   for (int r = r0; r < r1; ++r) {
     cudaLaunchConfig_t cfg = {};
