@@ -71,3 +71,20 @@ def test_size_helpers():
     assert O.size_to_fit((100, 50), 512) == (100, 50)
     with pytest.raises(ValueError):
         O.vgg_forward(torch.zeros(1, 3, 15, 40), O.make_vgg_weights(1), 'max', 29)
+
+
+def test_goldens_are_what_the_live_reference_produces(vgg_weights):
+    """Where the reference tree is present (build container: /root/reference, or the baseline/_ref install), re-run the
+    UNMODIFIED reference for one case and compare with the committed golden: the fixtures are not hand-edited and the
+    installed torch still reproduces them.  Skipped where no reference is available."""
+    from oracle import reference_harness as RH
+    if not RH.reference_available():
+        pytest.skip('no reference tree here')
+    name = 'max_64x48_single'
+    gold = np.load(GOLD / f'{name}.npz')
+    content, styles, pooling, kw = MG.build_case(name)
+    torch.manual_seed(0)
+    image, trace, _ = RH.run_reference(content, styles, vgg_weights, pooling=pooling, seed=0, **kw)
+    losses = np.array([t['loss'] for t in trace])
+    np.testing.assert_allclose(losses, gold['losses'], rtol=2e-5)   # thread count / oneDNN affect the last digits
+    assert np.abs(image.numpy() - gold['final_image']).mean() < 1e-4
