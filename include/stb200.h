@@ -106,6 +106,32 @@ STB_API int stb_adam_update(float* img, const float* grad, float* exp_avg, float
                             int row0, int rows, int64_t step, float lr, float beta1, float beta2, float adam_eps,
                             float ema_decay, void* stream);
 
+/* ------------------------------------------------------------------ tiled iteration, exchanges inside the library
+ * (csrc/comm.cu).  Each rank owns a MAILBOX (iteration stamps, its statistics block, its image gradient, its first /
+ * last 80 updated rows) that the peers map with CUDA IPC and read over NVLink; stb_iterate_banded is then the whole
+ * iteration of a band -- halo pull, forward, all-reduce of the statistics, backward, seam reduce of the gradient fused
+ * with Adam + clamp + EMA -- as ONE stream-ordered sequence (one CUDA graph), with no host call between its phases.
+ *   stb_comm_create        allocate the own mailbox for bands up to max_h_local x max_W (same numbers on every rank);
+ *                          ipc_handle_out64: 64-byte cudaIpcMemHandle_t to ship to the peers; mailbox_out: the pointer
+ *   stb_comm_connect_ipc   handles: world x 64 bytes in rank order (one process per GPU)
+ *   stb_comm_connect_local mailboxes[world]: device pointers of contexts living in THIS process (tests / emulation)
+ *   stb_comm_set_geometry  per scale: local height, first own row, own rows of this band; the neighbours' local
+ *                          heights and the first bottom-apron row of the upper one (all in their local coordinates)
+ *   stb_comm_reset         zero the iteration stamps; the host barriers over all ranks before AND after
+ * A peer that does not show up within 30 s makes the waiting kernel trap (CUDA error), it never hangs. */
+STB_API int stb_comm_create(stb_ctx* ctx, int rank, int world, int max_h_local, int max_W, void* ipc_handle_out64,
+                            void** mailbox_out);
+STB_API int stb_comm_connect_ipc(stb_ctx* ctx, const void* handles);
+STB_API int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes);
+STB_API int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_rows, int up_h_local,
+                                  int up_apron_row0, int dn_h_local);
+STB_API int stb_comm_reset(stb_ctx* ctx, void* stream);
+STB_API int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step,
+                               float lr, float beta1, float beta2, float adam_eps, float ema_decay,
+                               float* loss_out_host8, void* stream);
+/* 1: iterations replay as CUDA graphs, 2: enabled but nothing captured yet, 0: eager launches (note_out says why). */
+STB_API int stb_graph_status(stb_ctx* ctx, char* note_out, size_t note_bytes);
+
 /* ------------------------------------------------------------------ measurement (bench.py roofline leg)
  * CUDA-event timing per kernel class on the launching stream; classes in order: conv0_fwd_tv, conv_fwd, pool_fwd,
  * gram, sse, w2, conv_bwd, pool_bwd, conv0_bwd_adam, finalize (STB_PROF_CLASSES entries). */
@@ -113,32 +139,10 @@ STB_API int stb_adam_update(float* img, const float* grad, float* exp_avg, float
 STB_API int stb_profile_enable(stb_ctx* ctx, int enable);
 STB_API int stb_profile_read(stb_ctx* ctx, float* ms_out, int* count_out, int n_classes);
 
-/* ------------------------------------------------------------------ kernel test hooks (used by tests/ only) */
+/* ------------------------------------------------------------------ diagnostics
+ * Copy of an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward. */
 STB_API int stb_debug_activation(stb_ctx* ctx, int H, int W, int conv_index, void* out_bf16, size_t out_bytes,
                                  void* stream);
-STB_API int stb_pack_weights(const float* w_oihw, void* out_bf16, int Cout, int Cin, int bwd, void* stream);
-STB_API int stb_test_pixel_gemm(int H, int W, int Cin, int Cout, int C2, int mode, const void* A, const void* Bw,
-                                const void* A2, int a2_row0, int a2_rows, const void* B2, void* out,
-                                const float* bias, const void* mask_src, const void* ctarget, float cscale,
-                                int row_lo, int row_hi, void* stream);
-STB_API int stb_test_conv0_fwd(const float* img, const float* w0, const float* b0, void* out_bf16, int H, int W,
-                               float tv_weight, float* gtv, float* tv_partials, int* n_partials, void* stream);
-STB_API int stb_test_conv0_bwd(const void* g0_bf16, const float* w0, const float* gtv, float* grad_out, int H, int W,
-                               void* stream);
-/* conv 3x3 + bias + ReLU with the 2x2 pool fused into its epilogue (the product's only pool-forward path):
- * out [H][W][Cout] and pool_out [H/2][W/2][Cout], both bf16 NHWC. */
-STB_API int stb_test_conv_pool(int H, int W, int Cin, int Cout, const void* A, const void* Bw, const float* bias,
-                               void* out, void* pool_out, int pooling, void* stream);
-/* pool backward (+ ReLU mask of the pool input y): gin [H][W][C] from gout [H/2][W/2][C]. */
-STB_API int stb_test_pool_bwd(int pooling, const void* gout, const void* y, void* gin, int H, int W, int C,
-                              void* stream);
-STB_API int stb_test_gram(const void* F_bf16, long P, int C, float* partials_ws, size_t partials_floats,
-                          float* S_raw, float* sums, void* stream);
-STB_API size_t stb_test_gram_partials_floats(long P, int C);
-STB_API int stb_test_w2(const float* mean_t, const float* srm_t, const float* S_raw, const float* sums, int C,
-                        float npix, float weight, void* ws, size_t ws_bytes, float* loss_out, float* gs_out,
-                        float* gmu_out, float* csqrt_out, void* stream);
-STB_API size_t stb_test_w2_workspace_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,8 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / 'csrc'
 INCLUDE = PKG_DIR.parent / 'include'
 LIB_PATH = PKG_DIR / 'libstb200.so'
+TEST_LIB_PATH = PKG_DIR / 'libstb200_test.so'   # product objects + csrc/api_test.cu (kernel-level test hooks)
+TEST_ONLY_SOURCES = {'api_test.cu'}
 OBJ_DIR = PKG_DIR / 'build'
 
 NVCC_FLAGS = [
@@ -37,15 +39,16 @@ def sources() -> list[Path]:
 
 
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not TEST_LIB_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
+    t = min(LIB_PATH.stat().st_mtime, TEST_LIB_PATH.stat().st_mtime)
     deps = list(CSRC.glob('*')) + list(INCLUDE.glob('*.h')) + [Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu for sm_100a and link libstb200.so next to this file."""
+    """Compile every csrc/*.cu for sm_100a; link libstb200.so (product: everything but the test hooks) and
+    libstb200_test.so (the same objects + api_test.o, loaded by tests/ only) next to this file."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = _nvcc()
@@ -69,13 +72,16 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, sources()))
-    tmp = LIB_PATH.with_suffix('.so.tmp')
-    cmd = [nvcc, '-shared', '-cudart', 'static', '-o', str(tmp), *map(str, objs)]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
-    os.replace(tmp, LIB_PATH)
+        srcs = sources()
+        objs = list(ex.map(compile_one, srcs))
+    product = [o for o, src in zip(objs, srcs) if src.name not in TEST_ONLY_SOURCES]
+    for target, members in ((LIB_PATH, product), (TEST_LIB_PATH, objs)):
+        tmp = target.with_suffix('.so.tmp')
+        cmd = [nvcc, '-shared', '-cudart', 'static', '-o', str(tmp), *map(str, members)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+        os.replace(tmp, target)
     return LIB_PATH
 
 

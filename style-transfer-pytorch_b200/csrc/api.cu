@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -33,7 +34,7 @@ struct Plan {
   size_t g_off[2];             // gradient ping-pong
   size_t gtv_off, tvp_off, ssep_off, gramp_off, stats_off, loss_off, ctarget_off;
   size_t stats_layer_off[5];   // in floats, inside the stats block: S_raw then sums per layer
-  size_t stats_scalars = 0, stats_floats = 0;
+  size_t stats_scalars = 0, stats_floats = 0, gramp_floats = 0;
   size_t total = 0;
   int n_tv_partials = 0, n_sse_partials = 0;
 };
@@ -111,12 +112,26 @@ struct stb_ctx {
       exec = nullptr; key = GraphKey{}; hits = 0;
     }
   };
-  GraphSlot gslot[3];  // 0: stb_iterate, 1: stb_iterate_fwd, 2: stb_iterate_bwd (multi-GPU phases)
+  GraphSlot gslot[4];  // 0: stb_iterate, 1: stb_iterate_fwd, 2: stb_iterate_bwd (host-driven phases), 3: stb_iterate_banded
   void reset_graphs() { for (auto& g : gslot) g.reset(); }
   bool graphs_enabled = true;
+  std::string graph_note;  // why graph replay was switched off for this context (stb_graph_status)
   bool band_on = false;
   int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
+  // peer-memory exchange of the tiled iteration (comm.cu)
+  CommDev comm{};
+  bool comm_ready = false, comm_geometry = false, comm_ipc = false;
+  void* comm_mailbox = nullptr;       // own cudaMalloc block
+  size_t comm_bytes = 0;
+  int comm_max_h = 0, comm_max_w = 0;
 };
+
+// every ctx entry point runs on the context's device, whatever the caller's current device is
+#define STB_ENTER(ctx)                                                       \
+  do {                                                                       \
+    STB_CHECK((ctx) != nullptr, STB_ERR_INVALID, "null ctx");                \
+    STB_CUDA_CHECK(cudaSetDevice((ctx)->device));                            \
+  } while (0)
 
 namespace {
 
@@ -142,11 +157,11 @@ void make_plan(const stb_ctx* ctx, int H, int W, Plan* pl) {
   pl->n_tv_partials = ((W + 255) / 256) * H;
   pl->tvp_off = take((size_t)pl->n_tv_partials * 4);
   pl->ssep_off = take(1024 * 4);
+  // split-K partials of the Gram kernels: the bound over every pixel count, because a banded context launches them
+  // on its own rows only and the split count is not monotonic in the pixel count (~40 MB)
   size_t gp = 0;
-  for (int l = 0; l < 5; ++l) {
-    const int ci = kStyleConv[l];
-    gp = std::max(gp, gram_partials_floats((long)pl->h[ci] * pl->w[ci], kStyleC[l]));
-  }
+  for (int l = 0; l < 5; ++l) gp = std::max(gp, gram_max_partials_floats(kStyleC[l]));
+  pl->gramp_floats = gp;
   pl->gramp_off = take(gp * 4);
   size_t sf = 0;
   for (int l = 0; l < 5; ++l) { pl->stats_layer_off[l] = sf; sf += (size_t)kStyleC[l] * kStyleC[l] + kStyleC[l]; }
@@ -236,7 +251,7 @@ int style_grams(stb_ctx* ctx, const Plan& pl, cudaStream_t s) {
     float* S = stats + pl.stats_layer_off[l];
     const BandRows br = band_rows(ctx, pl, ci);
     STB_TRY(launch_gram(at<bf16>(ctx, pl.act_off[ci]) + (size_t)br.own0 * pl.w[ci] * C, (long)br.rows * pl.w[ci], C,
-                        at<float>(ctx, pl.gramp_off), S, S + (size_t)C * C, s));
+                        at<float>(ctx, pl.gramp_off), pl.gramp_floats, S, S + (size_t)C * C, s));
   }
   ctx->prof.end(s);
   return STB_OK;
@@ -331,7 +346,21 @@ __global__ void finalize_loss_kernel(const float* __restrict__ scalars, float co
 
 }  // namespace
 
+namespace {
+void comm_release(stb_ctx* ctx) {
+  if (ctx->comm_ipc)
+    for (int r = 0; r < ctx->comm.world; ++r)
+      if (r != ctx->comm.rank && ctx->comm.mbox[r]) cudaIpcCloseMemHandle(ctx->comm.mbox[r]);
+  if (ctx->comm_mailbox) cudaFree(ctx->comm_mailbox);
+  ctx->comm_mailbox = nullptr;
+  ctx->comm = CommDev{};
+  ctx->comm_ready = ctx->comm_geometry = ctx->comm_ipc = false;
+}
+}  // namespace
+
 extern "C" {
+
+const char* stb_last_error(void) { return last_error_string().c_str(); }
 
 int stb_ctx_create(int device, int pooling, const float* const* conv_w, const float* const* conv_b, void* stream,
                    stb_ctx** out) {
@@ -342,6 +371,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
   stb_ctx* ctx = new stb_ctx();
   ctx->device = device;
   ctx->pooling = pooling;
+  const int rc = [&]() -> int {
   size_t bytes = 0;
   for (int i = 0; i < NCONV; ++i) {
     bytes += align_up((size_t)kCout[i] * 4, 256);
@@ -349,7 +379,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
     else bytes += 2 * align_up((size_t)9 * kCout[i] * kCin[i] * 2, 256);
   }
   cudaError_t e = cudaMalloc(&ctx->owned, bytes);
-  if (e != cudaSuccess) { delete ctx; return set_error(STB_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  if (e != cudaSuccess) return set_error(STB_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
   uint8_t* p = static_cast<uint8_t*>(ctx->owned);
   auto take = [&](size_t b) { void* r = p; p += align_up(b, 256); return r; };
   for (int i = 0; i < NCONV; ++i) {
@@ -379,12 +409,20 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
   STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   STB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return STB_OK;
+  }();
+  if (rc != STB_OK) {  // nothing of a half-built context survives
+    stb_ctx_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return STB_OK;
 }
 
 void stb_ctx_destroy(stb_ctx* ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  comm_release(ctx);
   if (ctx->owned) cudaFree(ctx->owned);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -394,6 +432,7 @@ void stb_ctx_destroy(stb_ctx* ctx) {
 
 int stb_workspace_bytes(stb_ctx* ctx, int H, int W, size_t* bytes) {
   STB_CHECK(ctx && bytes, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_TRY(check_size(H, W, 0));
   Plan pl;
   make_plan(ctx, H, W, &pl);
@@ -406,6 +445,7 @@ int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream) {
   STB_CHECK(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 1023) == 0, STB_ERR_INVALID,
             "workspace must be a 1 KiB aligned device pointer");
   STB_CHECK(bytes >= ctx->w2_bytes + 4096, STB_ERR_WORKSPACE, "workspace smaller than the fixed W2 block");
+  STB_ENTER(ctx);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   STB_CUDA_CHECK(cudaStreamSynchronize(s));
   ctx->ws = static_cast<uint8_t*>(ptr);
@@ -420,6 +460,7 @@ int stb_bind_workspace(stb_ctx* ctx, void* ptr, size_t bytes, void* stream) {
 int stb_style_stats(stb_ctx* ctx, const float* img, int H, int W, float* const* mean_out, float* const* srm_out,
                     void* stream) {
   STB_CHECK(ctx && img && mean_out && srm_out, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_TRY(check_size(H, W, NCONV - 1));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan pl;
@@ -443,6 +484,7 @@ int stb_style_stats(stb_ctx* ctx, const float* img, int H, int W, float* const* 
 
 int stb_content_features(stb_ctx* ctx, const float* img, int H, int W, void* target_out_bf16, void* stream) {
   STB_CHECK(ctx && img && target_out_bf16, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_TRY(check_size(H, W, kContentConv));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan pl;
@@ -459,6 +501,7 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
                     const float* const* mean_t, const float* const* srm_t, const float* style_w, float tv_weight,
                     float eps, void* stream) {
   STB_CHECK(ctx && content_target_bf16 && mean_t && srm_t && style_w, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_TRY(check_size(H, W, NCONV - 1));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan pl;
@@ -618,7 +661,7 @@ int run_graphed(stb_ctx* ctx, int slot, const stb_ctx::GraphKey& key, bool allow
   if (++g.hits < 3) return run();  // eager first (lazy one-time setup must not happen inside a capture)
   cudaGraph_t graph = nullptr;
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
-    cudaGetLastError();
+    ctx->graph_note = std::string("cudaStreamBeginCapture failed: ") + cudaGetErrorString(cudaGetLastError());
     ctx->graphs_enabled = false;
     return run();
   }
@@ -626,10 +669,11 @@ int run_graphed(stb_ctx* ctx, int slot, const stb_ctx::GraphKey& key, bool allow
   const cudaError_t ce = cudaStreamEndCapture(s, &graph);
   if (rc != STB_OK || ce != cudaSuccess || graph == nullptr ||
       cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
-    cudaGetLastError();
+    ctx->graph_note = std::string("graph capture/instantiate failed (rc ") + std::to_string(rc) + ", " +
+                      cudaGetErrorString(ce) + " / " + cudaGetErrorString(cudaGetLastError()) + ")";
     if (graph) cudaGraphDestroy(graph);
     g.exec = nullptr;
-    ctx->graphs_enabled = false;  // fall back to eager launches for this context
+    ctx->graphs_enabled = false;  // eager launches from here on for this context; visible through stb_graph_status
     return run();
   }
   cudaGraphDestroy(graph);
@@ -644,6 +688,7 @@ int stb_iterate_ex(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, 
                    float beta1, float beta2, float adam_eps, float ema_decay, int apply_update, float* grad_out,
                    float* loss_out_host8, void* stream) {
   STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate");
   STB_CHECK(!(ctx->band_on && apply_update), STB_ERR_STATE,
             "banded contexts update through stb_iterate_fwd / all-reduce / stb_iterate_bwd / stb_adam_update");
@@ -700,6 +745,7 @@ int stb_stats_block(stb_ctx* ctx, int H, int W, float** dev_ptr, size_t* n_float
 
 int stb_iterate_fwd(stb_ctx* ctx, const float* img, void* stream) {
   STB_CHECK(ctx && img, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate_fwd");
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
@@ -712,6 +758,7 @@ int stb_iterate_fwd(stb_ctx* ctx, const float* img, void* stream) {
 
 int stb_iterate_bwd(stb_ctx* ctx, float* img, float* grad_out, float* loss_out_host8, void* stream) {
   STB_CHECK(ctx && img && grad_out, STB_ERR_INVALID, "null argument");
+  STB_ENTER(ctx);
   STB_CHECK(ctx->targets_set, STB_ERR_STATE, "stb_set_targets must precede stb_iterate_bwd");
   Plan pl;
   make_plan(ctx, ctx->tH, ctx->tW, &pl);
@@ -772,6 +819,172 @@ int stb_profile_read(stb_ctx* ctx, float* ms_out, int* count_out, int n_classes)
   ctx->prof.spans.clear();
   ctx->prof.used = 0;
   return STB_OK;
+}
+
+// ---- tiled iteration with the exchanges inside the library (comm.cu): ONE stream-ordered sequence, one CUDA graph
+//   begin (iteration stamp, wait for the neighbours' halo) -> halo pull -> forward + band-local statistics ->
+//   publish / all-reduce of the statistics over peer memory -> W2 + backward -> gradient stamp -> seam reduce +
+//   Adam + clamp + EMA + outbox fill -> halo stamp.
+// Mailbox = a cudaMalloc block of THIS library (CUDA IPC needs the allocation base); everything else stays torch-owned.
+int stb_comm_create(stb_ctx* ctx, int rank, int world, int max_h_local, int max_W, void* ipc_handle_out64,
+                    void** mailbox_out) {
+  STB_ENTER(ctx);
+  STB_CHECK(world >= 1 && world <= COMM_MAX_RANKS && rank >= 0 && rank < world, STB_ERR_INVALID,
+            "rank %d / world %d (at most %d ranks)", rank, world, COMM_MAX_RANKS);
+  STB_CHECK(max_h_local >= 16 && max_W >= 16, STB_ERR_INVALID, "bad mailbox capacity %dx%d", max_h_local, max_W);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  comm_release(ctx);
+  ctx->reset_graphs();
+  Plan pl;
+  make_plan(ctx, 16, 16, &pl);  // stats block size does not depend on the image size
+  size_t off[5];
+  ctx->comm_bytes = comm_mailbox_bytes(pl.stats_floats, max_h_local, max_W, off);
+  STB_CUDA_CHECK(cudaMalloc(&ctx->comm_mailbox, ctx->comm_bytes));
+  STB_CUDA_CHECK(cudaMemset(ctx->comm_mailbox, 0, ctx->comm_bytes));
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->comm.rank = rank; ctx->comm.world = world;
+  ctx->comm.off_stats[0] = off[0]; ctx->comm.off_stats[1] = off[1]; ctx->comm.off_grad = off[2];
+  ctx->comm.off_outbox[0] = off[3]; ctx->comm.off_outbox[1] = off[4];
+  ctx->comm.mbox[rank] = static_cast<uint8_t*>(ctx->comm_mailbox);
+  ctx->comm_max_h = max_h_local; ctx->comm_max_w = max_W;
+  if (ipc_handle_out64) {
+    cudaIpcMemHandle_t h;
+    STB_CUDA_CHECK(cudaIpcGetMemHandle(&h, ctx->comm_mailbox));
+    std::memcpy(ipc_handle_out64, &h, sizeof(h));
+  }
+  if (mailbox_out) *mailbox_out = ctx->comm_mailbox;
+  // every kernel of an iteration must be loaded before a peer-wait kernel can be resident (see comm_preload)
+  STB_TRY(comm_preload()); STB_TRY(preload_conv_kernels()); STB_TRY(preload_gram_kernels());
+  STB_TRY(preload_w2_kernels()); STB_TRY(preload_conv0_kernels()); STB_TRY(preload_image_kernels());
+  cudaFuncAttributes fa;
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(reduce2_kernel)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(adam_scalars_kernel)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(finalize_loss_kernel)));
+  return STB_OK;
+}
+
+// handles: world x 64 bytes (cudaIpcMemHandle_t of every rank's mailbox, rank order; own entry ignored)
+int stb_comm_connect_ipc(stb_ctx* ctx, const void* handles) {
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->comm_mailbox && handles, STB_ERR_STATE, "stb_comm_create first");
+  for (int r = 0; r < ctx->comm.world; ++r) {
+    if (r == ctx->comm.rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * r, sizeof(h));
+    void* p = nullptr;
+    STB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->comm.mbox[r] = static_cast<uint8_t*>(p);
+  }
+  ctx->comm_ipc = true;
+  ctx->comm_ready = true;
+  return STB_OK;
+}
+
+// same process (several contexts / streams, e.g. the single-GPU emulation of the tests): plain device pointers
+int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes) {
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->comm_mailbox && mailboxes, STB_ERR_STATE, "stb_comm_create first");
+  for (int r = 0; r < ctx->comm.world; ++r) {
+    STB_CHECK(mailboxes[r] != nullptr, STB_ERR_INVALID, "null mailbox of rank %d", r);
+    if (r == ctx->comm.rank) STB_CHECK(mailboxes[r] == ctx->comm_mailbox, STB_ERR_INVALID, "own mailbox mismatch");
+    else {
+      int peer_dev = -1;
+      cudaPointerAttributes pa;
+      STB_CUDA_CHECK(cudaPointerGetAttributes(&pa, mailboxes[r]));
+      peer_dev = pa.device;
+      if (peer_dev != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else STB_CUDA_CHECK(e);
+      }
+    }
+    ctx->comm.mbox[r] = static_cast<uint8_t*>(mailboxes[r]);
+  }
+  ctx->comm_ready = true;
+  return STB_OK;
+}
+
+// geometry of this band and of its neighbours for the current scale (rows in LOCAL coordinates of each rank)
+int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_rows, int up_h_local,
+                          int up_apron_row0, int dn_h_local) {
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->comm_mailbox, STB_ERR_STATE, "stb_comm_create first");
+  STB_CHECK(h_local <= ctx->comm_max_h && W <= ctx->comm_max_w && up_h_local <= ctx->comm_max_h &&
+                dn_h_local <= ctx->comm_max_h, STB_ERR_WORKSPACE, "band %dx%d exceeds the mailbox capacity %dx%d",
+            h_local, W, ctx->comm_max_h, ctx->comm_max_w);
+  const bool has_up = ctx->comm.rank > 0, has_dn = ctx->comm.rank + 1 < ctx->comm.world;
+  STB_CHECK(own_rows >= COMM_APRON && own0 == (has_up ? COMM_APRON : 0) &&
+                h_local == own0 + own_rows + (has_dn ? COMM_APRON : 0), STB_ERR_INVALID,
+            "band geometry: h_local=%d own0=%d own_rows=%d (aprons are %d rows)", h_local, own0, own_rows, COMM_APRON);
+  if (has_up) STB_CHECK(up_apron_row0 + COMM_APRON == up_h_local, STB_ERR_INVALID, "upper neighbour geometry");
+  ctx->comm.W = W; ctx->comm.h_local = h_local; ctx->comm.own0 = own0; ctx->comm.own_rows = own_rows;
+  ctx->comm.up_h_local = up_h_local; ctx->comm.up_apron_row0 = up_apron_row0; ctx->comm.dn_h_local = dn_h_local;
+  ctx->comm_geometry = true;
+  ctx->gslot[3].reset();
+  return STB_OK;
+}
+
+// zero the iteration stamps of the own mailbox.  The host must barrier over all ranks BEFORE (nobody still reads the
+// old stamps) and AFTER (nobody polls a mailbox that is not reset yet).
+int stb_comm_reset(stb_ctx* ctx, void* stream) {
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->comm_mailbox, STB_ERR_STATE, "stb_comm_create first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  STB_CUDA_CHECK(cudaMemsetAsync(ctx->comm_mailbox, 0, 4096, s));
+  STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return STB_OK;
+}
+
+int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
+                       float beta1, float beta2, float adam_eps, float ema_decay, float* loss_out_host8,
+                       void* stream) {
+  STB_CHECK(ctx && img && exp_avg && exp_avg_sq && ema && step >= 1, STB_ERR_INVALID, "bad argument");
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->targets_set && ctx->band_on, STB_ERR_STATE, "stb_set_band + stb_set_targets must precede");
+  STB_CHECK(ctx->comm_ready && ctx->comm_geometry, STB_ERR_STATE, "stb_comm_connect_* + stb_comm_set_geometry first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan pl;
+  make_plan(ctx, ctx->tH, ctx->tW, &pl);
+  STB_TRY(ensure_ws(ctx, pl));
+  const CommDev& c = ctx->comm;
+  STB_CHECK(c.h_local == pl.H && c.W == pl.W && c.own0 == ctx->band_own0 && c.own_rows == ctx->band_own_rows,
+            STB_ERR_STATE, "comm geometry (%dx%d, own %d+%d) does not match the band (%dx%d, own %d+%d)", c.h_local,
+            c.W, c.own0, c.own_rows, pl.H, pl.W, ctx->band_own0, ctx->band_own_rows);
+  if (ctx->dev_step_mirror != step - 1) {
+    const long long v = step - 1;
+    STB_CUDA_CHECK(cudaMemcpyAsync(ctx->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, s));
+    STB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  ctx->dev_step_mirror = step;
+  float* grad = reinterpret_cast<float*>(c.mbox[c.rank] + c.off_grad);
+  auto run = [&]() -> int {
+    STB_TRY(launch_comm_phase(c, 0, s));
+    STB_TRY(launch_halo_pull(c, img, s));
+    STB_TRY(iterate_fwd(ctx, pl, img, s));
+    STB_TRY(launch_stats_allreduce(c, at<float>(ctx, pl.stats_off), pl.stats_floats, s));
+    adam_scalars_kernel<<<1, 1, 0, s>>>(ctx->d_step, ctx->d_adam, lr, beta1, beta2, adam_eps, ema_decay);
+    STB_TRY(iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad, loss_out_host8, s));
+    STB_TRY(launch_comm_phase(c, 2, s));
+    STB_TRY(launch_adam_seam(c, img, exp_avg, exp_avg_sq, ema, ctx->d_adam, s));
+    return launch_comm_phase(c, 3, s);
+  };
+  stb_ctx::GraphKey key{};
+  key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img; key.m = exp_avg; key.v = exp_avg_sq; key.ema = ema;
+  key.loss = loss_out_host8; key.lr = lr; key.b1 = beta1; key.b2 = beta2; key.eps = adam_eps; key.decay = ema_decay;
+  return run_graphed(ctx, 3, key, true, s, run);
+}
+
+// 1: iterations replay as CUDA graphs; 0: eager launches (why: stb_last_error-style text in note_out, optional)
+int stb_graph_status(stb_ctx* ctx, char* note_out, size_t note_bytes) {
+  STB_CHECK(ctx != nullptr, STB_ERR_INVALID, "null ctx");
+  if (note_out && note_bytes > 0) {
+    std::strncpy(note_out, ctx->graph_note.c_str(), note_bytes - 1);
+    note_out[note_bytes - 1] = 0;
+  }
+  bool any = false;
+  for (const auto& g : ctx->gslot) any = any || g.exec != nullptr;
+  return ctx->graphs_enabled ? (any ? 1 : 2) : 0;  // 2: enabled, nothing captured yet
 }
 
 // test hook: copy an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward

@@ -1,13 +1,14 @@
 // Kernel-level C-ABI entry points used by tests/ (each wraps exactly one launcher so that the parity tests can
-// check every kernel against the oracle in isolation).  Declared in include/stb200.h under "kernel test hooks".
+// check every kernel against the oracle in isolation).  Declared in include/stb200_test.h; linked ONLY into
+// libstb200_test.so -- the product library libstb200.so does not contain this file.
 #include "kernels.h"
-#include "stb200.h"
+#include "stb200_test.h"
 
 using namespace stb;
 
 extern "C" {
 
-const char* stb_last_error(void) { return last_error_string().c_str(); }
+const char* stb_test_last_error(void) { return last_error_string().c_str(); }
 
 int stb_pack_weights(const float* w_oihw, void* out_bf16, int Cout, int Cin, int bwd, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -94,7 +95,7 @@ size_t stb_test_gram_partials_floats(long P, int C) { return gram_partials_float
 int stb_test_gram(const void* F_bf16, long P, int C, float* partials_ws, size_t partials_floats, float* S_raw,
                   float* sums, void* stream) {
   STB_CHECK(partials_floats >= gram_partials_floats(P, C), STB_ERR_WORKSPACE, "gram partials workspace too small");
-  return launch_gram(static_cast<const bf16*>(F_bf16), P, C, partials_ws, S_raw, sums,
+  return launch_gram(static_cast<const bf16*>(F_bf16), P, C, partials_ws, partials_floats, S_raw, sums,
                      static_cast<cudaStream_t>(stream));
 }
 

@@ -448,6 +448,14 @@ int launch_conv0_fwd(const float* img, const bf16* w0_packed, const float* bias,
 
 namespace stb {
 
+int preload_conv0_kernels() {
+  cudaFuncAttributes fa;
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(conv0_fwd_kernel)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(conv0_bwd_kernel)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(pack_w0_bwd_q_kernel)));
+  return STB_OK;
+}
+
 int pack_weights_conv0_bwd(const float* w0, bf16* out, cudaStream_t s) {
   pack_w0_bwd_q_kernel<<<8, 256, 0, s>>>(w0, out);
   STB_CUDA_CHECK(cudaGetLastError());

@@ -487,6 +487,19 @@ __global__ void pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ ou
 }  // namespace
 
 
+// Force the (lazily loaded) kernels of this file into the context: a first launch may need a context-wide
+// synchronisation, which must not happen while a peer-wait kernel of the tiled path is resident (comm.cu).
+int preload_conv_kernels() {
+  cudaFuncAttributes fa;
+#define STB_PRELOAD(k) STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)))
+  STB_PRELOAD((pixel_gemm_kernel<64, 0>)); STB_PRELOAD((pixel_gemm_kernel<64, 1>)); STB_PRELOAD((pixel_gemm_kernel<64, 2>));
+  STB_PRELOAD((pixel_gemm_kernel<128, 0>)); STB_PRELOAD((pixel_gemm_kernel<128, 1>)); STB_PRELOAD((pixel_gemm_kernel<128, 2>));
+  STB_PRELOAD((pixel_gemm_kernel<256, 0>)); STB_PRELOAD((pixel_gemm_kernel<256, 1>)); STB_PRELOAD((pixel_gemm_kernel<256, 2>));
+  STB_PRELOAD(pack_w_kernel);
+#undef STB_PRELOAD
+  return STB_OK;
+}
+
 int pack_weights_fwd(const float* w, bf16* out, int Cout, int Cin, cudaStream_t s) {
   pack_w_kernel<<<256, 256, 0, s>>>(w, out, Cout, Cin, 0);
   STB_CUDA_CHECK(cudaGetLastError());

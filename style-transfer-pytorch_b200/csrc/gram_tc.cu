@@ -268,6 +268,15 @@ int launch_gram_cfg(const CUtensorMap& tm, const GParams& gp, int n_tiles, int n
 
 }  // namespace
 
+int preload_gram_kernels() {
+  cudaFuncAttributes fa;
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(gram_kernel<64>)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(gram_kernel<128>)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(gram_kernel<256>)));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(gram_reduce_kernel)));
+  return STB_OK;
+}
+
 static int gram_pk(int BN) { return BN == 64 ? 256 : (BN == 128 ? 128 : 64); }
 
 int gram_num_splits(long P, int C) {
@@ -292,8 +301,23 @@ int gram_num_splits(long P, int C) {
 
 size_t gram_partials_floats(long P, int C) { return (size_t)gram_num_splits(P, C) * ((size_t)C * C + C); }
 
-int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream) {
+// Upper bound of gram_partials_floats over EVERY pixel count: gram_num_splits is not monotonic in P (a band of own rows
+// can need more splits than the taller local image the plan was sized for), so the workspace reserves this bound.
+size_t gram_max_partials_floats(int C) {
+  const int BN = C >= 256 ? 256 : C;
+  const int n_tiles = ((C + 127) / 128) * (C / BN);
+  long want = (num_sms() + n_tiles - 1) / n_tiles;
+  if (BN == 256) want *= 2;
+  if (want > 1024) want = 1024;
+  return (size_t)want * ((size_t)C * C + C);
+}
+
+int launch_gram(const bf16* F, long P, int C, float* partials_ws, size_t partials_capacity_floats, float* S_raw,
+                float* sums, cudaStream_t stream) {
   STB_CHECK(C % 64 == 0 && C <= 512 && P > 0, STB_ERR_INVALID, "gram: C=%d P=%ld", C, P);
+  STB_CHECK(gram_partials_floats(P, C) <= partials_capacity_floats, STB_ERR_WORKSPACE,
+            "gram: split-K partials need %zu floats, %zu reserved (P=%ld, C=%d)", gram_partials_floats(P, C),
+            partials_capacity_floats, P, C);
   const int BN = C >= 256 ? 256 : C;
   const int n_tj = C / BN;
   const int n_ti = (C + 127) / 128;

@@ -422,6 +422,16 @@ int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int
   return STB_OK;
 }
 
+int preload_image_kernels() {
+  cudaFuncAttributes fa;
+#define STB_PRELOAD(k) STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)))
+  STB_PRELOAD(tv_kernel); STB_PRELOAD(pack_w0_fwd_kernel); STB_PRELOAD(conv0_bwd_adam_kernel);
+  STB_PRELOAD(pool_bwd_kernel<STB_POOL_MAX>); STB_PRELOAD(pool_bwd_kernel<STB_POOL_AVERAGE>);
+  STB_PRELOAD(pool_bwd_kernel<STB_POOL_L2>); STB_PRELOAD(sse_kernel);
+#undef STB_PRELOAD
+  return STB_OK;
+}
+
 int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s) {
   const long n8 = n / 8;
   int g = grid_for(n8, 256);

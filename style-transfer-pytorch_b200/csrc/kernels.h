@@ -73,8 +73,10 @@ int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_par
 // ---------------------------------------------------------------- Gram / channel sums on tcgen05 (gram_tc.cu)
 int gram_num_splits(long P, int C);
 size_t gram_partials_floats(long P, int C);
+size_t gram_max_partials_floats(int C);  // bound of gram_partials_floats over every P (what the workspace reserves)
 // F: [P][C] bf16 pixel-major.  S_raw [C][C] and sums [C] receive the un-normalised sums over the P pixels.
-int launch_gram(const bf16* F, long P, int C, float* partials_ws, float* S_raw, float* sums, cudaStream_t stream);
+int launch_gram(const bf16* F, long P, int C, float* partials_ws, size_t partials_capacity_floats, float* S_raw,
+                float* sums, cudaStream_t stream);
 
 // ---------------------------------------------------------------- W2 style loss engine (w2_tc.cu)
 // Every matrix of the chain is 4 fp32 planes of n*n floats: hi, lo (3xTF32 split) and the same for its transpose.
@@ -126,5 +128,33 @@ struct W2Engine {
   int forward_backward(float* loss_terms, cudaStream_t s);  // S_raw/sums -> loss_terms[5], gs_bf16, gmu_bias
   static int read_matrix(float* dst, const float* pair, int n, cudaStream_t s);  // dst = hi + lo (test hook)
 };
+
+// ---------------------------------------------------------------- multi-GPU peer-memory exchange (comm.cu)
+constexpr int COMM_APRON = 80;       // halo rows on each interior side of a band (receptive-field radius of relu5_1)
+constexpr int COMM_MAX_RANKS = 8;
+// u64 slots at the head of a mailbox (one 128-byte line each)
+enum { COMM_ITER = 0, COMM_FLAG_STATS = 16, COMM_FLAG_GRAD = 32, COMM_FLAG_HALO = 48, COMM_ERR = 64 };
+struct CommDev {  // passed by value to the exchange kernels
+  int rank, world;
+  uint8_t* mbox[COMM_MAX_RANKS];   // mailbox of every rank as mapped into THIS process (own one included)
+  size_t off_stats[2], off_grad, off_outbox[2];
+  int W, h_local, own0, own_rows;           // this band: local image height, first own row, number of own rows
+  int up_h_local, up_apron_row0, dn_h_local;  // neighbours' local heights; first bottom-apron row of the upper band
+};
+size_t comm_mailbox_bytes(size_t stats_floats, int max_h_local, int max_W, size_t off[5]);
+int launch_comm_phase(const CommDev& c, int phase, cudaStream_t s);   // 0 begin, 1 stats, 2 grad, 3 end
+int launch_halo_pull(const CommDev& c, float* img, cudaStream_t s);
+int launch_stats_allreduce(const CommDev& c, float* stats, size_t n_floats, cudaStream_t s);
+int launch_adam_seam(const CommDev& c, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
+                     const AdamScalars* d_adam, cudaStream_t s);
+
+// force every kernel of the library into the context (lazy module loading may otherwise synchronise the context at
+// a first launch, which deadlocks against a resident peer-wait kernel)
+int comm_preload();
+int preload_conv_kernels();
+int preload_gram_kernels();
+int preload_w2_kernels();
+int preload_conv0_kernels();
+int preload_image_kernels();
 
 }  // namespace stb

@@ -415,6 +415,16 @@ __global__ void sum_planes_kernel(float* __restrict__ dst, const float* __restri
 
 }  // namespace
 
+int preload_w2_kernels() {
+  cudaFuncAttributes fa;
+#define STB_PRELOAD(k) STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)))
+  STB_PRELOAD(w2_gemm_kernel); STB_PRELOAD(w2_cov_kernel); STB_PRELOAD(w2_ns_init_kernel);
+  STB_PRELOAD(w2_target_finish_kernel); STB_PRELOAD(w2_fwd_finish_kernel); STB_PRELOAD(w2_bwd_finish_kernel);
+  STB_PRELOAD(w2_gmu_kernel); STB_PRELOAD(sum_planes_kernel);
+#undef STB_PRELOAD
+  return STB_OK;
+}
+
 int W2Engine::read_matrix(float* dst, const float* pair, int n, cudaStream_t s) {
   sum_planes_kernel<<<64, 256, 0, s>>>(dst, pair, (size_t)n * n);
   STB_CUDA_CHECK(cudaGetLastError());

@@ -34,7 +34,12 @@ CASES = {
     'max_128_noise_tv': dict(content=(6, 128, 128, 96), styles=[(7, 64, 100, 128)], pooling='max',
                              kw=dict(min_scale=128, end_scale=128, initial_iterations=3, tv_weight=5.0,
                                      content_weight=0.05, style_scale_fac=0.75)),
+    # BASELINE.json configs[1]: 512 x 512 end_scale, default multi-scale (128, 181, 256, 362, 512), iteration counts
+    # cut from 1000 + 4 x 500 to 20 + 4 x 10
+    'max_pyramid_128_512': dict(content=(1, 16, 512, 512), styles=[(2, 32, 512, 512)], pooling='max',
+                                kw=dict(min_scale=128, end_scale=512, iterations=10, initial_iterations=20)),
 }
+QUANTISED_FINAL = {'max_pyramid_128_512'}  # final image stored as floor(x * 255) uint8 (what get_image() returns)
 
 
 def build_case(name):
@@ -46,16 +51,23 @@ def build_case(name):
 
 def main():
     weights = O.make_vgg_weights(1234)
+    only = set(sys.argv[1:])
     for name in CASES:
+        if only and name not in only:
+            continue
         content, styles, pooling, kw = build_case(name)
         torch.manual_seed(0)
         image, trace, st = R.run_reference(content, styles, weights, pooling=pooling, seed=0, **kw)
         losses = np.array([t['loss'] for t in trace], dtype=np.float64)
         sizes = np.array([(t['w'], t['h'], t['i'], t['i_max']) for t in trace], dtype=np.int32)
-        np.savez_compressed(OUT / f'{name}.npz', losses=losses, sizes=sizes,
-                            final_image=image.numpy().astype(np.float32))
+        final = image.numpy().astype(np.float32)
+        if name in QUANTISED_FINAL:
+            final = np.floor(final * 255).astype(np.uint8)
+        np.savez_compressed(OUT / f'{name}.npz', losses=losses, sizes=sizes, final_image=final)
         print(name, losses[:3], '...', losses[-1], image.shape, flush=True)
 
+    if only and 'max_64x48_internals' not in only:
+        return
     # single-iteration internals for the first case: per-term losses and d loss/d image from reference autograd
     ref = R.import_reference()
     content, styles, pooling, kw = build_case('max_64x48_single')

@@ -10,12 +10,17 @@ DEV = torch.device('cuda:0')
 
 
 def lib():
-    return _lib.load()
+    """libstb200_test.so: kernel-level hooks (include/stb200_test.h).  The product library is reached through the
+    `style_transfer_b200` package (gpu_util.make_st / st.model.lib)."""
+    return _lib.load_test()
 
 
 P = _lib.ptr
 S = _lib.cur_stream
-check = _lib.check
+
+
+def check(rc):
+    _lib.check(rc, test_lib=True)
 
 
 def rel_err(got, ref):

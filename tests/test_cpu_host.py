@@ -15,16 +15,28 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_library_exports_every_declared_symbol():
+    """libstb200.so exports exactly what include/stb200.h declares; the kernel-level test hooks live in a separate
+    library (libstb200_test.so / include/stb200_test.h) and are NOT exported by the product."""
     import __graft_entry__ as ge
     ge.build()
-    hdr = (ROOT / 'include' / 'stb200.h').read_text()
-    declared = set(re.findall(r'STB_API\s+[\w\s\*]+?\b(stb_\w+)\s*\(', hdr))
-    assert len(declared) >= 20
+    from style_transfer_b200 import _lib
+    pat = r'STB_API\s+[\w\s\*]+?\b(stb_\w+)\s*\('
+    declared = set(re.findall(pat, (ROOT / 'include' / 'stb200.h').read_text()))
+    declared_test = set(re.findall(pat, (ROOT / 'include' / 'stb200_test.h').read_text()))
+    assert len(declared) >= 20 and len(declared_test) >= 10
     lib = ctypes.CDLL(str(ROOT / 'style-transfer-pytorch_b200' / 'libstb200.so'))
+    tlib = ctypes.CDLL(str(ROOT / 'style-transfer-pytorch_b200' / 'libstb200_test.so'))
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in stb200.h but not exported'
-    from style_transfer_b200 import _lib
+    for name in declared_test:
+        assert hasattr(tlib, name), f'{name} declared in stb200_test.h but not exported by the test library'
+        assert not hasattr(lib, name), f'test hook {name} leaked into the product library'
     assert declared == set(_lib.EXPORTS)
+    assert declared_test == set(_lib.TEST_EXPORTS)
+    out = subprocess.run(['nm', '-D', '--defined-only', str(ROOT / 'style-transfer-pytorch_b200' / 'libstb200.so')],
+                         capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ' T ' in ln and ln.split()[-1].startswith('stb_')}
+    assert exported == declared, exported ^ declared
 
 
 def test_product_does_not_touch_the_oracle():

@@ -18,7 +18,7 @@ from oracle import st_oracle as O  # noqa: E402
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
-lib = _lib.load()
+lib = _lib.load_test()
 P = _lib.ptr
 S = _lib.cur_stream
 ALL_OK = True

@@ -9,8 +9,8 @@ import torch
 import torch.nn.functional as F
 
 ROOT = Path(__file__).resolve().parent.parent
-lib = ctypes.CDLL(str(ROOT / 'style-transfer-pytorch_b200' / 'libstb200.so'))
-lib.stb_last_error.restype = ctypes.c_char_p
+lib = ctypes.CDLL(str(ROOT / 'style-transfer-pytorch_b200' / 'libstb200_test.so'))
+lib.stb_test_last_error.restype = ctypes.c_char_p
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
@@ -26,7 +26,7 @@ def stream():
 
 def check(rc):
     if rc != 0:
-        raise RuntimeError(f'rc={rc}: {lib.stb_last_error().decode()}')
+        raise RuntimeError(f'rc={rc}: {lib.stb_test_last_error().decode()}')
 
 
 def pack(w, bwd):

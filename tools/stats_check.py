@@ -53,7 +53,7 @@ for li, layer in enumerate((1, 6)):
 # ---- the native W2 engine alone, fed with the fp64 oracle statistics (cast to fp32)
 import ctypes
 from style_transfer_b200 import _lib
-lib = m.lib
+lib = _lib.load_test()
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 for li, layer in enumerate((1, 6)):
     f = acts_b[layer]
