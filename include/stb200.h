@@ -123,6 +123,7 @@ STB_API int stb_comm_create(stb_ctx* ctx, int rank, int world, int max_h_local, 
                             void** mailbox_out);
 STB_API int stb_comm_connect_ipc(stb_ctx* ctx, const void* handles);
 STB_API int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes);
+STB_API int stb_comm_disconnect(stb_ctx* ctx);  /* unmap the peers' mailboxes (host barrier, then re-create) */
 STB_API int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_rows, int up_h_local,
                                   int up_apron_row0, int dn_h_local);
 STB_API int stb_comm_reset(stb_ctx* ctx, void* stream);

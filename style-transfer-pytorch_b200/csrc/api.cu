@@ -844,6 +844,11 @@ int stb_comm_create(stb_ctx* ctx, int rank, int world, int max_h_local, int max_
   STB_CUDA_CHECK(cudaMemset(ctx->comm_mailbox, 0, ctx->comm_bytes));
   STB_CUDA_CHECK(cudaDeviceSynchronize());
   ctx->comm.rank = rank; ctx->comm.world = world;
+  {
+    const char* e = getenv("STB_COMM_TIMEOUT_S");
+    const double sec = e ? atof(e) : 30.0;
+    ctx->comm.timeout_ns = (unsigned long long)((sec > 0.1 ? sec : 0.1) * 1e9);
+  }
   ctx->comm.off_stats[0] = off[0]; ctx->comm.off_stats[1] = off[1]; ctx->comm.off_grad = off[2];
   ctx->comm.off_outbox[0] = off[3]; ctx->comm.off_outbox[1] = off[4];
   ctx->comm.mbox[rank] = static_cast<uint8_t*>(ctx->comm_mailbox);
@@ -902,6 +907,22 @@ int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes) {
     ctx->comm.mbox[r] = static_cast<uint8_t*>(mailboxes[r]);
   }
   ctx->comm_ready = true;
+  return STB_OK;
+}
+
+// unmap the peers' mailboxes (before any rank frees / re-creates its own; the host barriers in between)
+int stb_comm_disconnect(stb_ctx* ctx) {
+  STB_ENTER(ctx);
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->reset_graphs();
+  if (ctx->comm_ipc)
+    for (int r = 0; r < ctx->comm.world; ++r)
+      if (r != ctx->comm.rank && ctx->comm.mbox[r]) {
+        STB_CUDA_CHECK(cudaIpcCloseMemHandle(ctx->comm.mbox[r]));
+        ctx->comm.mbox[r] = nullptr;
+      }
+  ctx->comm_ipc = false;
+  ctx->comm_ready = false;
   return STB_OK;
 }
 

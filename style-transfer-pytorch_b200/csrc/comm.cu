@@ -20,7 +20,7 @@
 //                       deterministic, and bit-identical on every rank, so the replicated W2 chain stays in lock step
 //   adam_seam_kernel    seam reduce of the image gradient (own + neighbours' apron rows) fused with Adam + clamp + EMA
 //                       (torch/optim/adam.py:413-546, ST:483-486) and with the fill of the outboxes
-// A wait that is not satisfied within COMM_TIMEOUT_NS traps (the launch fails with a CUDA error) instead of hanging.
+// A wait that is not satisfied within CommDev::timeout_ns (30 s; STB_COMM_TIMEOUT_S) traps (the launch fails with a CUDA error) instead of hanging.
 #include <cstring>
 
 #include "kernels.h"
@@ -29,8 +29,6 @@
 namespace stb {
 
 namespace {
-
-constexpr unsigned long long COMM_TIMEOUT_NS = 30ull * 1000 * 1000 * 1000;
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -58,12 +56,13 @@ __device__ __forceinline__ void unpack(const float& v, float (&a)[1]) { a[0] = v
 __device__ __forceinline__ void pack(float4& v, const float (&a)[4]) { v = make_float4(a[0], a[1], a[2], a[3]); }
 __device__ __forceinline__ void pack(float& v, const float (&a)[1]) { v = a[0]; }
 
-__device__ void wait_stamp(const unsigned long long* flag, unsigned long long want, unsigned long long* err) {
+__device__ void wait_stamp(const unsigned long long* flag, unsigned long long want, unsigned long long* err,
+                           unsigned long long timeout_ns) {
   if (ld_acquire_sys(flag) >= want) return;
   const unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
   while (ld_acquire_sys(flag) < want) {
-    if ((++spins & 0xFF) == 0 && globaltimer_ns() - t0 > COMM_TIMEOUT_NS) {
+    if ((++spins & 0xFF) == 0 && globaltimer_ns() - t0 > timeout_ns) {
       *err = want;
       __threadfence_system();
       __trap();
@@ -91,9 +90,9 @@ __global__ void comm_phase_kernel(CommDev c, int phase) {
   if (phase == 3 || lane >= c.world || lane == c.rank) return;
   const bool neighbour = lane == c.rank - 1 || lane == c.rank + 1;
   const unsigned long long* peer = reinterpret_cast<const unsigned long long*>(c.mbox[lane]);
-  if (phase == 0 && neighbour) wait_stamp(peer + COMM_FLAG_HALO, t - 1, own + COMM_ERR);
-  if (phase == 1) wait_stamp(peer + COMM_FLAG_STATS, t, own + COMM_ERR);
-  if (phase == 2 && neighbour) wait_stamp(peer + COMM_FLAG_GRAD, t, own + COMM_ERR);
+  if (phase == 0 && neighbour) wait_stamp(peer + COMM_FLAG_HALO, t - 1, own + COMM_ERR, c.timeout_ns);
+  if (phase == 1) wait_stamp(peer + COMM_FLAG_STATS, t, own + COMM_ERR, c.timeout_ns);
+  if (phase == 2 && neighbour) wait_stamp(peer + COMM_FLAG_GRAD, t, own + COMM_ERR, c.timeout_ns);
 }
 
 // halo rows of the local image <- the neighbours' outboxes (skipped in the first iteration after a reset: the halo

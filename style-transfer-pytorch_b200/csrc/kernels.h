@@ -140,6 +140,7 @@ struct CommDev {  // passed by value to the exchange kernels
   size_t off_stats[2], off_grad, off_outbox[2];
   int W, h_local, own0, own_rows;           // this band: local image height, first own row, number of own rows
   int up_h_local, up_apron_row0, dn_h_local;  // neighbours' local heights; first bottom-apron row of the upper band
+  unsigned long long timeout_ns;              // a peer wait longer than this traps instead of hanging
 };
 size_t comm_mailbox_bytes(size_t stats_floats, int max_h_local, int max_W, size_t off[5]);
 int launch_comm_phase(const CommDev& c, int phase, cudaStream_t s);   // 0 begin, 1 stats, 2 grad, 3 end

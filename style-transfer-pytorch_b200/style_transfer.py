@@ -10,6 +10,7 @@ the iteration loop (ST:472-486) runs in the native library.  There is no CPU or 
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 import warnings
 from dataclasses import dataclass
@@ -130,6 +131,7 @@ class NativeVGG:
             _lib.check(self.lib.stb_ctx_create(device.index or 0, _lib.POOLING[pooling], wp, bp, _lib.cur_stream(),
                                                ctypes.byref(self.ctx)))
         self._ws = None
+        self._ws_bound = 0
 
     def __del__(self):
         try:
@@ -148,18 +150,20 @@ class NativeVGG:
     def ensure_workspace(self, sizes):
         """Bind a torch-owned workspace large enough for every (h, w) in sizes.  Returns True if (re)bound."""
         need = max(self.workspace_bytes(h, w) for h, w in sizes)
-        if self._ws is not None and self._ws.numel() >= need + 1024:
+        if self._ws is not None and need <= self._ws_bound:   # compare with what the context was actually given
             return False
         self._ws = None
         torch.cuda.empty_cache()  # hand the old block back before asking for the bigger one
         self._ws = torch.empty(need + 2048, dtype=torch.uint8, device=self.device)
         base = self._ws.data_ptr()
         aligned = (base + 1023) // 1024 * 1024
-        _lib.check(self.lib.stb_bind_workspace(self.ctx, ctypes.c_void_p(aligned), need, _lib.cur_stream()))
+        self._ws_bound = self._ws.numel() - (aligned - base)    # bind everything usable, not just `need`
+        _lib.check(self.lib.stb_bind_workspace(self.ctx, ctypes.c_void_p(aligned), self._ws_bound, _lib.cur_stream()))
         return True
 
     def release_workspace(self):
         self._ws = None
+        self._ws_bound = 0
 
     # ------------------------------------------------------------------ target extraction
     def _check_image(self, image):
@@ -209,6 +213,43 @@ class NativeVGG:
                                             _lib.ptr(ema), h, w, row0, rows, step, lr, 0.9, 0.99, 1e-8, avg_decay,
                                             _lib.cur_stream()))
 
+    # ------------------------------------------------------------------ peer-memory exchange (csrc/comm.cu)
+    def comm_create(self, rank, world, max_h_local, max_w):
+        """Allocate this rank's mailbox; returns (64-byte CUDA IPC handle, device pointer)."""
+        handle = ctypes.create_string_buffer(64)
+        p = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.stb_comm_create(self.ctx, rank, world, max_h_local, max_w, handle, ctypes.byref(p)))
+        return handle.raw, p.value
+
+    def comm_connect_ipc(self, handles):
+        blob = b''.join(handles)
+        _lib.check(self.lib.stb_comm_connect_ipc(self.ctx, blob))
+
+    def comm_connect_local(self, pointers):
+        arr = (ctypes.c_void_p * len(pointers))(*pointers)
+        _lib.check(self.lib.stb_comm_connect_local(self.ctx, ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))))
+
+    def comm_disconnect(self):
+        _lib.check(self.lib.stb_comm_disconnect(self.ctx))
+
+    def comm_set_geometry(self, w, band, up, down):
+        _lib.check(self.lib.stb_comm_set_geometry(self.ctx, w, band.h_local, band.own0, band.own_rows,
+                                                  up.h_local if up else 0, up.own0 + up.own_rows if up else 0,
+                                                  down.h_local if down else 0))
+
+    def comm_reset(self):
+        _lib.check(self.lib.stb_comm_reset(self.ctx, _lib.cur_stream()))
+
+    def iterate_banded(self, image, exp_avg, exp_avg_sq, ema, step, lr, avg_decay, loss_host):
+        _lib.check(self.lib.stb_iterate_banded(self.ctx, _lib.ptr(image), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                               _lib.ptr(ema), step, lr, 0.9, 0.99, 1e-8, avg_decay,
+                                               _lib.ptr(loss_host), _lib.cur_stream()))
+
+    def graph_status(self):
+        note = ctypes.create_string_buffer(512)
+        return self.lib.stb_graph_status(self.ctx, note, 512), note.value.decode(errors='replace')
+
     def set_targets(self, h, w, content_target, content_weight, means, srms, layer_weights, tv_weight, eps=1e-4):
         mp, _k1 = _lib.ptr_array(means)
         sp, _k2 = _lib.ptr_array(srms)
@@ -231,11 +272,16 @@ class StyleTransfer:
 
         if len(self.devices) not in (1, 2):
             raise ValueError('Only 1 or 2 devices are supported.')
-        if any(d.type != 'cuda' for d in self.devices):
-            raise RuntimeError('style-transfer-pytorch_b200 runs its hot path only on CUDA (sm_100a) devices; '
-                               f'got devices={[str(d) for d in self.devices]}. There is no CPU fallback.')
         if not torch.cuda.is_available():
-            raise RuntimeError('CUDA is not available; the B200-native hot path cannot run.')
+            raise RuntimeError('CUDA is not available; the B200-native hot path cannot run (there is no CPU '
+                               'fallback).')
+        if any(d.type != 'cuda' for d in self.devices):
+            # the reference's default argument is devices=['cpu'] (ST:310): call sites that rely on it keep working,
+            # on the GPU this implementation exists for -- loudly, never on a CPU path
+            warnings.warn('style-transfer-pytorch_b200 runs its hot path only on CUDA (sm_100a) devices; '
+                          f'devices={[str(d) for d in self.devices]} -> using cuda:{torch.cuda.current_device()} '
+                          '(there is no CPU fallback)')
+            self.devices = [torch.device('cuda', torch.cuda.current_device())]
         if len(self.devices) == 2:
             warnings.warn('the reference\'s 2-device layer split (ST:326-333) is superseded; running on '
                           f'{self.devices[0]} only')
@@ -250,17 +296,29 @@ class StyleTransfer:
         # iterations run on a dedicated (non-legacy) stream so that the library can replay them as a CUDA graph
         self._stream = torch.cuda.Stream(device=dev)
         self.last_loss_terms = None
-        # one process per GPU under torch.distributed: large scales are tiled spatially over the ranks
-        import torch.distributed as dist
-        self._dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if distributed is not None:
-            self._dist = bool(distributed) and self._dist
-        self._rank = dist.get_rank() if self._dist else 0
-        self._world = dist.get_world_size() if self._dist else 1
+        # one process per GPU under torch.distributed: large scales are tiled spatially over the ranks.
+        # `distributed`: None = the torch.distributed default group if initialised, False = never tile, or a group
+        # object (distributed.TorchGroup / ThreadGroup).
+        if distributed is None or distributed is True:
+            self._group = D.default_group()
+        elif distributed is False:
+            self._group = None
+        else:
+            self._group = distributed
+        self._dist = self._group is not None and self._group.world > 1
+        self._rank = self._group.rank if self._dist else 0
+        self._world = self._group.world if self._dist else 1
+        self._comm_mode = os.environ.get('STB_COMM', 'peer')   # 'peer': exchanges inside the library; 'nccl': host-driven
+        self._comm_cap = None
+        self._band = None
 
     # ------------------------------------------------------------------ results
     def get_image_tensor(self):
-        return self.average.get().detach()[0].clamp(0, 1)
+        self._stream.synchronize()   # iterations run on the library's stream; the EMA must be complete before it is read
+        value = self.average.get().detach()
+        if self._band is not None:   # tiled scale in flight: the average holds this rank's rows only (collective call)
+            value = D.gather_rows(value, self._band, self._group)
+        return value[0].clamp(0, 1)
 
     def get_image(self, image_type='pil'):
         if self.average is None:
@@ -310,16 +368,88 @@ class StyleTransfer:
         self.average.note_update()
 
     def _iterate_banded(self, band, stats, grad, exp_avg, exp_avg_sq, step, lr, avg_decay):
-        """One iteration of a spatially tiled scale: this rank's band + the three exchanges (distributed.py)."""
+        """One iteration of a spatially tiled scale.  'peer' mode: one library call = one CUDA graph holding the
+        compute AND the three exchanges (kernels reading the peers' mailboxes over NVLink, csrc/comm.cu).  'nccl' mode
+        (fallback): the host drives the phases and NCCL moves the data."""
         m = self.model
-        m.iterate_fwd(self.image)
-        torch.distributed.all_reduce(stats)             # Gram sums, channel sums, content SSE, TV sum
-        m.iterate_bwd(self.image, grad, self._loss_host)
-        D.exchange_add_grad(grad, band)                 # seam reduce of the image gradient
-        m.adam_update(self.image, grad, exp_avg, exp_avg_sq, self.average.value, band.own0, band.own_rows, step, lr,
-                      avg_decay)
-        D.exchange_halo(self.image, band)               # refresh the halo rows of the iterate
+        if self._comm_mode == 'peer':
+            m.iterate_banded(self.image, exp_avg, exp_avg_sq, self.average.value, step, lr, avg_decay, self._loss_host)
+        else:
+            m.iterate_fwd(self.image)
+            torch.distributed.all_reduce(stats)             # Gram sums, channel sums, content SSE, TV sum
+            m.iterate_bwd(self.image, grad, self._loss_host)
+            D.exchange_add_grad(grad, band)                 # seam reduce of the image gradient
+            m.adam_update(self.image, grad, exp_avg, exp_avg_sq, self.average.value, band.own0, band.own_rows, step,
+                          lr, avg_decay)
+            D.exchange_halo(self.image, band)               # refresh the halo rows of the iterate
         self.average.note_update()
+
+    def _setup_comm(self, band, w, cap_h, cap_w):
+        """Per tiled scale (collective over the ranks): make sure the mailboxes exist and are mapped by the peers, zero
+        the iteration stamps between two barriers, hand the band geometry to the library."""
+        g, m = self._group, self.model
+        if self._comm_mode == 'peer' and (self._comm_cap is None or self._comm_cap[0] < cap_h or self._comm_cap[1] < cap_w):
+            ok, mine, err = True, None, None
+            try:
+                if self._comm_cap is not None:
+                    m.comm_disconnect()          # nobody may still map a mailbox that is about to be freed
+            except _lib.NativeError as e:
+                ok, err = False, e
+            g.barrier()
+            try:
+                handle, pointer = m.comm_create(self._rank, self._world, cap_h, cap_w)
+                mine = handle if g.peer_kind == 'ipc' else pointer
+            except _lib.NativeError as e:
+                ok, err = False, e
+            infos = g.all_gather_object((ok, mine))       # every rank takes the same branch from here on
+            if all(i[0] for i in infos):
+                try:
+                    if g.peer_kind == 'ipc':
+                        m.comm_connect_ipc([i[1] for i in infos])
+                    else:
+                        m.comm_connect_local([i[1] for i in infos])
+                except _lib.NativeError as e:
+                    ok, err = False, e
+            else:
+                ok = False
+            if all(g.all_gather_object(ok)):
+                self._comm_cap = (cap_h, cap_w)
+            else:
+                warnings.warn(f'peer-memory exchange unavailable on some rank ({err}); falling back to host-driven '
+                              'NCCL exchanges')
+                self._comm_mode = 'nccl'
+        if self._comm_mode != 'peer':
+            return
+        bands = D.all_bands(band.H, self._world)
+        g.barrier()
+        m.comm_reset()
+        g.barrier()
+        up = bands[self._rank - 1] if self._rank > 0 else None
+        down = bands[self._rank + 1] if self._rank + 1 < self._world else None
+        m.comm_set_geometry(w, band, up, down)
+
+    def _style_stats(self, simg, sh, sw):
+        """(means, second raw moments) of one style image (ST:440-443).  Under torch.distributed a large style image
+        is tiled like the iterate: every rank runs its band, the raw sums are all-reduced once (per scale, not per
+        iteration), and the global pixel counts normalise them."""
+        m = self.model
+        band = D.make_band(sh, self._rank, self._world) if self._dist else None
+        if band is None:
+            m.set_band(False)
+            return m.style_stats(simg)
+        m.set_band(True, sh, band.own0, band.own_rows)
+        means, srms = m.style_stats(D.local_slice(simg, band))      # RAW sums over this band's own rows
+        m.set_band(False)
+        flat = torch.cat([t.flatten() for t in means + srms])
+        self._group.all_reduce_sum(flat)
+        counts = D.tap_pixel_counts(sh, sw)
+        out, off = [], 0
+        for t in means + srms:
+            out.append(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        means = [t / n for t, n in zip(out[:5], counts)]
+        srms = [t / n for t, n in zip(out[5:], counts)]
+        return means, srms
 
     def loss_and_grad(self):
         """Closure of ST:472-476 evaluated natively on the current image: returns (terms[8] host tensor, grad)."""
@@ -367,6 +497,8 @@ class StyleTransfer:
             self.image = first_content.clone()
         else:
             self.image = self._initial_image(init, content_image, style_images, style_weights, cw, ch).to(dev)
+            if self._dist:  # random inits are drawn per process: every rank continues from rank 0's draw
+                self._group.broadcast(self.image, 0)
 
         exp_avg = exp_avg_sq = None
         step = 0
@@ -392,7 +524,12 @@ class StyleTransfer:
                 band = D.make_band(ch, self._rank, self._world) if (self._dist and optimizer == 'adam') else None
                 h_loc = band.h_local if band is not None else ch
                 self.model.set_band(False)
-                self.model.ensure_workspace([(h_loc, cw)] + [(sh, sw) for sw, sh, _ in styles])
+                self._band = None
+                style_sizes = []
+                for sw, sh, _ in styles:   # a tiled style image needs room for its band only
+                    sb = D.make_band(sh, self._rank, self._world) if self._dist else None
+                    style_sizes.append((sb.h_local if sb is not None else sh, sw))
+                self.model.ensure_workspace([(h_loc, cw)] + style_sizes)
 
                 self.image = _resize(self.image.detach(), (ch, cw), 'bicubic').clamp_(0, 1).contiguous()
                 if band is not None:
@@ -406,7 +543,7 @@ class StyleTransfer:
                 means = srms = None
                 for weight, (sw, sh, simg) in zip(style_weights, styles):
                     print(f'Processing style image ({sw}x{sh})...')
-                    m_i, s_i = self.model.style_stats(simg)
+                    m_i, s_i = self._style_stats(simg, sh, sw)
                     if means is None:
                         means = [m * weight for m in m_i]
                         srms = [s * weight for s in s_i]
@@ -419,6 +556,12 @@ class StyleTransfer:
                     self.model.set_band(True, ch, band.own0, band.own_rows)
                 self.model.set_targets(h_loc, cw, content_target, per_content_weight, means, srms, self.style_weights,
                                        tv_weight)
+                if band is not None:
+                    # mailboxes are sized once for the largest scale of this call (the last one)
+                    ew, eh = size_to_fit(content_image.size, scales[-1], scale_up=True)
+                    cap_h = max(b.h_local for b in D.all_bands(eh, self._world))
+                    self._setup_comm(band, cw, max(cap_h, h_loc), max(ew, cw))
+                    self._band = band
 
                 if optimizer == 'adam':
                     if exp_avg is None:
@@ -430,8 +573,10 @@ class StyleTransfer:
                     if band is not None:
                         if exp_avg.shape[2] != h_loc:
                             exp_avg, exp_avg_sq = D.local_slice(exp_avg, band), D.local_slice(exp_avg_sq, band)
-                        stats = self.model.stats_view(h_loc, cw)
-                        grad = torch.empty_like(self.image)
+                        stats = grad = None
+                        if self._comm_mode != 'peer':   # host-driven exchanges need torch views of both
+                            stats = self.model.stats_view(h_loc, cw)
+                            grad = torch.empty_like(self.image)
                 else:
                     lbfgs = self._make_lbfgs()
                 torch.cuda.empty_cache()
@@ -461,8 +606,11 @@ class StyleTransfer:
                                            gpu_ram=gpu_ram))
 
                 if band is not None:  # stitch the bands back together (identical full tensors on every rank)
-                    self.average = EMA.from_state(D.gather_rows(self.average.value, band), self.average.accum, avg_decay)
-                    exp_avg, exp_avg_sq = D.gather_rows(exp_avg, band), D.gather_rows(exp_avg_sq, band)
+                    self._band = None
+                    g = self._group
+                    self.average = EMA.from_state(D.gather_rows(self.average.value, band, g), self.average.accum,
+                                                  avg_decay)
+                    exp_avg, exp_avg_sq = D.gather_rows(exp_avg, band, g), D.gather_rows(exp_avg_sq, band, g)
                     self.image = self.average.get()
                     self.model.set_band(False)
                 else:
