@@ -15,12 +15,15 @@ native arm   value   = it/s of K stb_iterate calls, state resident in HBM, CUDA 
              roofline= conv tensor-pipe: algorithmic conv FLOPs per iteration / summed duration of the tcgen05 conv
                        launches (CUDA events around every launch, second instrumented pass), vs the measured
                        sustained bf16 peak of MEASURED_PEAKS.json.
-             cpu_baseline = the oracle port (same torch-CPU primitives the reference's CPU path uses) timed on the
-                       host cores on a bounded sample, extrapolated with an affine cost model in pixels.
-reference arm (--impl reference): the CPU baseline alone, printed in the same JSON shape.
-N > 1: ONE 2048x2048 job tiled spatially over the N GPUs (strong scaling): horizontal bands with 80-row halo aprons,
-one NCCL all-reduce of the 2.4 MB statistics block, a seam exchange of the image gradient and a halo refresh of the
-image per iteration (style-transfer-pytorch_b200/distributed.py).
+             cpu_baseline = the UNMODIFIED reference (baseline/_ref; else the oracle port) timed on all host cores for one
+                       real iteration at the benchmark size after a warm-up iteration (no extrapolation).
+reference arm (--impl reference): 2-3 real 2048^2 iterations of the reference's CPU path + configs[0] (256^2, 50
+                       iterations), printed in the same JSON shape.
+N > 1: ONE 2048x2048 job tiled spatially over the N GPUs (strong scaling): horizontal bands with 80-row halo aprons;
+per iteration one all-reduce of the 2.4 MB statistics block, a seam reduce of the image gradient (fused with Adam)
+and a halo pull, all as kernels reading the peers' mailboxes over NVLink inside ONE CUDA graph per rank
+(style-transfer-pytorch_b200/csrc/comm.cu, distributed.py).  The line then carries
+`parity_vs_n1`: the tiled loss trace against rank 0's untiled run of the same job.
 """
 import argparse
 import json
@@ -103,73 +106,91 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_port_iteration_time(size, iters, warm):
-    """Seconds per iteration of the oracle port at size x size on the host cores (all threads torch uses)."""
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core (the reference's CPU path does)."""
     import torch
-    from oracle import st_oracle as O
-    wts = O.make_vgg_weights(1234)
-    content, style = O.synth_image(1, 16, size, size), O.synth_image(2, 32, size, size)
-    tg, _ = O.make_targets(content, [style], [1.0], size, wts, 'max', 0.015, 2.0)
-    st = O.IterState.fresh(O.to_tensor(content))
-    times = []
-    for i in range(warm + iters):
-        t0 = time.perf_counter()
-        O.iterate(st, wts, tg, 'max')
-        times.append(time.perf_counter() - t0)
-    times = sorted(times[warm:])
-    return times[len(times) // 2], torch.get_num_threads()
+    n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
-def cpu_reference_iteration_time(size, iters):
-    """Seconds per iteration of the UNMODIFIED reference's stylize() on the host cores (baseline/_ref install)."""
+class _Budget(Exception):
+    pass
+
+
+def reference_iteration_times(size, n_iters, budget_s):
+    """Per-iteration wall times of the UNMODIFIED reference's stylize() (single scale, size x size, CPU) when its
+    install travelled with the repo (baseline/_ref), else of the oracle port of the same loop body.  Returns
+    (kind, [seconds per iteration, first one excluded], threads).  Stops early once budget_s is exceeded."""
     import torch
     from oracle import reference_harness as RH
     from oracle import st_oracle as O
+    threads = _use_all_host_threads()
     wts = O.make_vgg_weights(1234)
     content, style = O.synth_image(1, 16, size, size), O.synth_image(2, 32, size, size)
-    t, _ = RH.time_reference(size, iters, wts, content, style, devices=('cpu',))
-    return t, torch.get_num_threads()
-
-
-def cpu_baseline(size, budget_s=25.0):
-    """Affine model t(px) = a + b*px from two bounded samples (the W2/sqrtm part, ~65 GFLOP, does not scale with
-    pixels; the conv part does), evaluated at size^2.  Times the unmodified reference (kind "reference") when its
-    install travelled with the repo (baseline/_ref), else the oracle port of the same loop body (kind "port")."""
-    from oracle import reference_harness as RH
+    stamps = []
+    t_start = time.perf_counter()
     if RH.reference_available():
-        kind, what = 'reference', 'unmodified reference StyleTransfer.stylize(devices=[cpu]), median of STIterate.time diffs'
-        timer, its = cpu_reference_iteration_time, 3
+        kind = 'reference'
+        ref = RH.import_reference()
+
+        def cb(it):
+            stamps.append(it.time)   # ST:493
+            if len(stamps) >= 2 and time.perf_counter() - t_start > budget_s:
+                raise _Budget()
+
+        torch.manual_seed(0)
+        with RH.patched_checkpoint(wts):
+            st = ref.StyleTransfer(devices=['cpu'], pooling='max')
+        import contextlib
+        import io
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                st.stylize(content, [style], min_scale=size, end_scale=size, initial_iterations=n_iters + 1, callback=cb)
+        except _Budget:
+            pass
     else:
-        kind, what = 'port', 'oracle port (torch-CPU explicit schedule), median'
-        timer, its = (lambda size_, n: cpu_port_iteration_time(size_, n, 1)), 2
-    # two bounded samples; the larger one as close to the target size as the time budget allows (cache effects make
-    # the small sizes optimistic)
-    small = 256
-    t256, threads = timer(small, its)
-    big = 512
-    for cand in (1024, 768):
-        if t256 * (cand * cand) / (small * small) * (its + 3) < budget_s:
-            big = cand
-            break
-    tbig, _ = timer(big, its)
-    b = (tbig - t256) / (big * big - small * small)
-    a = max(t256 - b * small * small, 0.0)
-    t_full = a + b * size * size
-    return dict(value=1.0 / t_full, unit='it/s', cores=threads, kind=kind,
-                sample=f'{what}: {small}^2 ({t256:.3f} s/it) and {big}^2 ({tbig:.3f} s/it), affine-in-pixels '
-                       f'extrapolation to {size}^2 ({t_full:.2f} s/it)')
+        kind = 'port'
+        tg, _ = O.make_targets(content, [style], [1.0], size, wts, 'max', 0.015, 2.0)
+        state = O.IterState.fresh(O.to_tensor(content))
+        for _ in range(n_iters + 1):
+            O.iterate(state, wts, tg, 'max')
+            stamps.append(time.time())
+            if len(stamps) >= 2 and time.perf_counter() - t_start > budget_s:
+                break
+    return kind, [b - a for a, b in zip(stamps[:-1], stamps[1:])], threads
+
+
+def cpu_baseline(size, n_iters=1, budget_s=90.0):
+    """The reference's CPU path on the host cores, REAL iterations at the benchmark size (no extrapolation)."""
+    kind, dts, threads = reference_iteration_times(size, n_iters, budget_s)
+    dts = sorted(dts)
+    med = dts[len(dts) // 2]
+    what = ('unmodified reference StyleTransfer.stylize(devices=[cpu])' if kind == 'reference'
+            else 'oracle port (torch-CPU explicit schedule)')
+    return dict(value=1.0 / med, unit='it/s', cores=threads, kind=kind,
+                sample=f'{what}: {len(dts)} timed iteration(s) at {size}x{size} after one warm-up iteration, '
+                       f'median {med:.2f} s/it (all: {[round(d, 2) for d in dts]})')
 
 
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb = cpu_baseline(args.size, budget_s=60.0)
+    # a bounded sample of the SAME workload: real 2048^2 iterations of the reference on all host threads
+    n = max(2, min(args.steps, 3))
+    cb = cpu_baseline(args.size, n_iters=n, budget_s=150.0)
+    # BASELINE.json configs[0]: 256 x 256, 50 iterations, single scale, --devices cpu
+    kind0, d0, _ = reference_iteration_times(256, 50, 60.0)
+    d0 = sorted(d0)
     line = dict(metric='stylize iterations/sec at end_scale=2048', value=cb['value'], unit='it/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / cb['value'], higher_is_better=True,
                 scaling='strong', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'{args.size}x{args.size} single scale, pooling=max, content+1 style, '
-                                     'CPU reference path (' + cb['kind'] + ')'),
+                                     'CPU reference path (' + cb['kind'] + '), real iterations at this size',
+                            config0=dict(workload='256x256 single scale, 50 iterations (BASELINE.json configs[0])',
+                                         kind=kind0, it_per_s=1.0 / d0[len(d0) // 2], iterations_timed=len(d0))),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit='it/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -195,20 +216,25 @@ def run_native(args, rank, local_rank, world):
     m = st.model
     band = D.make_band(size, rank, world) if world > 1 else None
     h_loc = band.h_local if band is not None else size
-    m.ensure_workspace([(h_loc, size), (size, size)])
-    cimg = O.to_tensor(content).to(dev)
+    cimg_full = O.to_tensor(content).to(dev)
     simg = O.to_tensor(style).to(dev)
-    means, srms = m.style_stats(simg)
+    sband = D.make_band(size, rank, world) if world > 1 else None
+    m.ensure_workspace([(h_loc, size), (sband.h_local if sband is not None else size, size)])
+    means, srms = st._style_stats(simg, size, size)   # tiled over the ranks like the iterate when world > 1
+    cimg = cimg_full
     if band is not None:
-        cimg = D.local_slice(cimg, band)
+        cimg = D.local_slice(cimg_full, band)
         m.set_band(True, size, band.own0, band.own_rows)
     ct = m.content_features(cimg)
     m.set_targets(h_loc, size, ct, 0.015, means, srms, st.style_weights, 2.0)
+    if band is not None:
+        st._setup_comm(band, size, max(b.h_local for b in D.all_bands(size, world)), size)
     st.image = cimg.clone()
     st.average = stb.style_transfer.EMA(st.image, 0.99)
     ea, eas = torch.zeros_like(st.image), torch.zeros_like(st.image)
     step = 0
-    if band is not None:
+    stats = grad = None
+    if band is not None and st._comm_mode != 'peer':
         stats, grad = m.stats_view(h_loc, size), torch.empty_like(st.image)
 
     def one_iteration():
@@ -227,43 +253,85 @@ def run_native(args, rank, local_rank, world):
     side = torch.cuda.Stream(device=dev)  # non-legacy stream: lets the library replay iterations as a CUDA graph
     side.wait_stream(torch.cuda.current_stream(dev))
     torch.cuda.set_stream(side)
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up; the first PARITY_ITS of it double as the multi-GPU parity check (loss read back every iteration)
+    PARITY_ITS = 5
+    head = []
+    for i in range(max(args.warmup, 3, PARITY_ITS)):
         one_iteration()
+        if i < PARITY_ITS:
+            side.synchronize()
+            head.append(float(st._loss_host[0]))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        one_iteration()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    # ---- REPEATS timed regions of exactly `steps` iterations each (barrier + synchronize on both sides, CUDA events,
+    # max over ranks per region); the reported value is the MEDIAN region, the others are listed
+    REPEATS = 5
+    region_ms = []
+    r0, k0, _ = m.launch_count()
+    for _ in range(REPEATS):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one_iteration()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms.append(float(t.item()))
+    r1, k1, per_graph = m.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(st._loss_host[0])
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = sorted(region_ms)[len(region_ms) // 2]
     ms_per_step = ms_total / args.steps
     tiled = band is not None
     # tiled: all ranks advanced ONE job by `steps` iterations; otherwise (N == 1) the single job
     value = args.steps / (ms_total / 1000.0)
+    # kernels launched inside the timed regions of THIS rank, counted from the captured graphs' kernel nodes
+    launches_per_step = (k1 - k0) / max(1, REPEATS * args.steps)
+    graph_ok, graph_note = m.graph_status()
+
+    # ---- multi-GPU parity: rank 0 re-runs the first iterations of the SAME job untiled on its own GPU
+    parity = None
+    if tiled:
+        if rank == 0:
+            st1 = stb.StyleTransfer(devices=[str(dev)], pooling='max', vgg_weights=wts, distributed=False)
+            m1 = st1.model
+            m1.ensure_workspace([(size, size)])
+            mm, ss = m1.style_stats(simg)
+            ct1 = m1.content_features(cimg_full)
+            m1.set_targets(size, size, ct1, 0.015, mm, ss, st1.style_weights, 2.0)
+            st1.image = cimg_full.clone()
+            st1.average = stb.style_transfer.EMA(st1.image, 0.99)
+            a1, b1 = torch.zeros_like(st1.image), torch.zeros_like(st1.image)
+            ref_head = []
+            for i in range(PARITY_ITS):
+                st1._iterate(a1, b1, i + 1, 0.02, 0.99, True)
+                torch.cuda.current_stream().synchronize()
+                ref_head.append(float(st1._loss_host[0]))
+            rel = [abs(a - b) / abs(b) for a, b in zip(head, ref_head)]
+            parity = dict(iterations=PARITY_ITS, tiled_losses=head, single_gpu_losses=ref_head,
+                          max_rel_diff=max(rel), ok=max(rel) < 5e-4,
+                          note='loss trace of the N-way tiled run vs the untiled run of the same job on rank 0')
+            del st1, m1
+            torch.cuda.empty_cache()
+        barrier()
 
     # ---- instrumented pass: per-kernel-class device time (events around every launch)
     prof = None
     if rank == 0:
         _lib.check(m.lib.stb_profile_enable(m.ctx, 1))
         n_prof = min(args.steps, 10)
+        g_prof = grad if grad is not None else torch.empty_like(st.image)
         for _ in range(n_prof):
             if band is None:
                 one_iteration()
-            else:  # instrumented compute only (no collectives inside the event spans' critical path on rank 0)
-                step += 1
+            else:  # instrumented compute only (no exchanges inside the event spans' critical path on rank 0)
                 m.iterate_fwd(st.image)
-                m.iterate_bwd(st.image, grad, st._loss_host)
+                m.iterate_bwd(st.image, g_prof, st._loss_host)
         torch.cuda.synchronize()
         ms = (ctypes.c_float * 10)()
         cnt = (ctypes.c_int * 10)()
@@ -311,39 +379,53 @@ def run_native(args, rank, local_rank, world):
         conv_ms = prof['conv_fwd']['ms_per_iter'] + prof['conv_bwd']['ms_per_iter']
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks['bf16_tflops_sustained']
-        # kernels per iteration: counted from the ncu launch list of one eager iteration
-        # (profiles/r1_launches_2048_v11.csv: 24 conv + 52 W2 rounds + 5 W2 helpers + 5 Gram + 5 reduce + conv0 fwd/bwd
-        # + border + TV + 4 pool bwd + SSE + 3 scalar/finalize kernels = 104); the tiled path adds adam_rows
-        launches = 104 + (1 if tiled else 0)
-        traffic = None
-        tpath = ROOT / 'profiles' / 'r1_conv_traffic.json'
-        if tpath.exists() and size == 2048 and world == 1:
-            traffic = json.loads(tpath.read_text())['dram_total_bytes']  # dram read+write of the conv launches, ncu
+        traffic, traffic_src = None, None
+        for cand in ('r2_conv_traffic.json', 'r1_conv_traffic.json'):
+            tpath = ROOT / 'profiles' / cand
+            if tpath.exists() and size == 2048 and world == 1:
+                traffic = json.loads(tpath.read_text())['dram_total_bytes']  # dram read+write of the conv launches, ncu
+                traffic_src = f'profiles/{cand} (one ncu --set full capture of the same command; not measured in this run)'
+                break
         roofline = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-                        traffic=traffic, peak_source=f"{peaks['source']} (bf16_tflops_sustained)",
+                        traffic=traffic, traffic_source=traffic_src,
+                        peak_source=f"{peaks['source']} (bf16_tflops_sustained)",
+                        frac_of_burst_peak=achieved / peaks['bf16_tflops'],
                         kernel='pixel_gemm_kernel (tcgen05 conv fwd+dgrad incl. tap-gradient GEMMs, 25 launches/iter)',
                         note='algorithmic FLOPs/iter of the twelve 3x3 convs (1437696/pixel) / summed CUDA-event duration of the conv '
-                             'launches in an instrumented pass; traffic = DRAM bytes (read+write) of the same launches per '
-                             'iteration from one ncu --set full capture (profiles/r1_ncu_conv_v11.csv; algorithmic ~8.5 GB)',
+                             'launches in an instrumented pass of this run',
                         step_fraction=conv_ms / sum(v['ms_per_iter'] for v in prof.values()),
                         classes_ms_per_iter={k: round(v['ms_per_iter'], 4) for k, v in prof.items()},
                         whole_step_tensor_frac=CONV_FLOP_PER_PIXEL * size * size * (1000.0 / ms_per_step) / 1e12 /
                         (peak * world))
         cb = None
         if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0, N = 1 only
-            cb = cpu_baseline(size)
+            cb = cpu_baseline(size, n_iters=1, budget_s=60.0)
+        par = 'single GPU'
+        if tiled:
+            par = (f'{world}-way spatial tiling: bands of {band.own_rows}+{band.top_apron + band.bottom_apron} halo rows '
+                   f'(rank 0); exchanges = ' +
+                   ('peer-memory kernels inside the iteration graph (stats all-reduce, seam reduce fused with Adam, '
+                    'halo pull; CUDA IPC over NVLink)' if st._comm_mode == 'peer' else
+                    'host-driven NCCL (1 all-reduce + 2 send/recv per iteration)'))
         line = dict(metric='stylize iterations/sec at end_scale=2048', value=value, unit='it/s', n_gpus=world,
-                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
-                    scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic', impl='native',
+                    steps=args.steps, warmup=max(args.warmup, 3, PARITY_ITS), ms_per_step=ms_per_step,
+                    higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic',
+                    impl='native',
                     config=dict(workload=f'{size}x{size} single scale (BASELINE.json configs[2]), pooling=max, '
                                          'content+1 style, bf16 operands / fp32 accumulate, fp32 sqrtm+Adam',
-                                parallelism='single GPU' if world == 1 else
-                                f'{world}-way spatial tiling: bands of {band.own_rows}+{band.top_apron + band.bottom_apron} '
-                                'halo rows (rank 0), 1 stats all-reduce + grad seam exchange + halo refresh per iteration',
+                                parallelism=par,
                                 l2='working set per iteration (>= 2.4 GB of activations) far exceeds the 126 MB L2',
-                                final_loss=final_loss),
-                    clocks=clocks, e2e=e2e, gpu_launches=int(round(launches * args.steps)), roofline=roofline,
-                    cpu_baseline=cb)
+                                final_loss=final_loss,
+                                timing=f'median of {REPEATS} timed regions of {args.steps} iterations each',
+                                regions_ms=[round(x, 3) for x in region_ms]),
+                    clocks=clocks, e2e=e2e,
+                    gpu_launches=int(round(launches_per_step * args.steps)),
+                    gpu_launches_note=f'{launches_per_step:.1f} kernels per iteration, counted from the kernel nodes of '
+                                      f'the replayed CUDA graph (per graph slot: {per_graph}); graph replay '
+                                      f'{"on" if graph_ok == 1 else "OFF: " + graph_note}',
+                    roofline=roofline, cpu_baseline=cb)
+        if parity is not None:
+            line['parity_vs_n1'] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

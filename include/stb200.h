@@ -132,6 +132,9 @@ STB_API int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* 
                                float* loss_out_host8, void* stream);
 /* 1: iterations replay as CUDA graphs, 2: enabled but nothing captured yet, 0: eager launches (note_out says why). */
 STB_API int stb_graph_status(stb_ctx* ctx, char* note_out, size_t note_bytes);
+/* Kernel launches issued through graph replays so far, counted from the captured graphs: number of replays, kernels
+ * they launched, kernel nodes per graph slot {stb_iterate, stb_iterate_fwd, stb_iterate_bwd, stb_iterate_banded}. */
+STB_API int stb_launch_count(stb_ctx* ctx, int64_t* graph_replays, int64_t* kernels_replayed, int* kernels_per_graph4);
 
 /* ------------------------------------------------------------------ measurement (bench.py roofline leg)
  * CUDA-event timing per kernel class on the launching stream; classes in order: conv0_fwd_tv, conv_fwd, pool_fwd,

@@ -55,6 +55,7 @@ def _declare(lib):
         'stb_comm_reset': [vp, vp],
         'stb_iterate_banded': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, vp, vp],
         'stb_graph_status': [vp, C.c_char_p, sz],
+        'stb_launch_count': [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i)],
         'stb_profile_enable': [vp, i],
         'stb_profile_read': [vp, C.POINTER(f), C.POINTER(i), i],
         'stb_debug_activation': [vp, i, i, i, vp, sz, vp],
@@ -90,7 +91,7 @@ EXPORTS = [
     'stb_set_band', 'stb_stats_block', 'stb_iterate_fwd', 'stb_iterate_bwd', 'stb_adam_update',
     'stb_comm_create', 'stb_comm_connect_ipc', 'stb_comm_connect_local', 'stb_comm_disconnect',
     'stb_comm_set_geometry', 'stb_comm_reset',
-    'stb_iterate_banded', 'stb_graph_status', 'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation',
+    'stb_iterate_banded', 'stb_graph_status', 'stb_launch_count', 'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation',
 ]
 # include/stb200_test.h (libstb200_test.so)
 TEST_EXPORTS = [

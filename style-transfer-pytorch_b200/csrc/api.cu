@@ -106,16 +106,18 @@ struct stb_ctx {
   struct GraphSlot {
     GraphKey key{};
     int hits = 0;
+    int kernel_nodes = 0;   // kernel launches one replay stands for (counted from the captured graph)
     cudaGraphExec_t exec = nullptr;
     void reset() {
       if (exec) cudaGraphExecDestroy(exec);
-      exec = nullptr; key = GraphKey{}; hits = 0;
+      exec = nullptr; key = GraphKey{}; hits = 0; kernel_nodes = 0;
     }
   };
   GraphSlot gslot[4];  // 0: stb_iterate, 1: stb_iterate_fwd, 2: stb_iterate_bwd (host-driven phases), 3: stb_iterate_banded
   void reset_graphs() { for (auto& g : gslot) g.reset(); }
   bool graphs_enabled = true;
   std::string graph_note;  // why graph replay was switched off for this context (stb_graph_status)
+  long long graph_replays = 0, kernels_replayed = 0;   // stb_launch_count
   bool band_on = false;
   int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
   // peer-memory exchange of the tiled iteration (comm.cu)
@@ -656,6 +658,8 @@ int run_graphed(stb_ctx* ctx, int slot, const stb_ctx::GraphKey& key, bool allow
   }
   if (g.exec) {
     STB_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+    ctx->graph_replays += 1;
+    ctx->kernels_replayed += g.kernel_nodes;
     return STB_OK;
   }
   if (++g.hits < 3) return run();  // eager first (lazy one-time setup must not happen inside a capture)
@@ -676,8 +680,21 @@ int run_graphed(stb_ctx* ctx, int slot, const stb_ctx::GraphKey& key, bool allow
     ctx->graphs_enabled = false;  // eager launches from here on for this context; visible through stb_graph_status
     return run();
   }
+  {  // how many kernel launches one replay stands for
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      if (cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) {
+          cudaGraphNodeType t;
+          if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g.kernel_nodes += 1;
+        }
+    }
+  }
   cudaGraphDestroy(graph);
   STB_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+  ctx->graph_replays += 1;
+  ctx->kernels_replayed += g.kernel_nodes;
   return STB_OK;
 }
 
@@ -1006,6 +1023,17 @@ int stb_graph_status(stb_ctx* ctx, char* note_out, size_t note_bytes) {
   bool any = false;
   for (const auto& g : ctx->gslot) any = any || g.exec != nullptr;
   return ctx->graphs_enabled ? (any ? 1 : 2) : 0;  // 2: enabled, nothing captured yet
+}
+
+// Kernel launches issued through graph replays so far (counted from the captured graphs, not assumed): replays,
+// kernels those replays launched, and the kernel nodes of each of the four graph slots (0 where nothing is captured).
+int stb_launch_count(stb_ctx* ctx, int64_t* graph_replays, int64_t* kernels_replayed, int* kernels_per_graph4) {
+  STB_CHECK(ctx != nullptr, STB_ERR_INVALID, "null ctx");
+  if (graph_replays) *graph_replays = ctx->graph_replays;
+  if (kernels_replayed) *kernels_replayed = ctx->kernels_replayed;
+  if (kernels_per_graph4)
+    for (int i = 0; i < 4; ++i) kernels_per_graph4[i] = ctx->gslot[i].kernel_nodes;
+  return STB_OK;
 }
 
 // test hook: copy an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward

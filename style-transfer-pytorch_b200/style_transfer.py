@@ -250,6 +250,12 @@ class NativeVGG:
         note = ctypes.create_string_buffer(512)
         return self.lib.stb_graph_status(self.ctx, note, 512), note.value.decode(errors='replace')
 
+    def launch_count(self):
+        """(graph replays, kernels launched by them, kernel nodes per graph slot) -- counted from the captured graphs."""
+        a, b, per = ctypes.c_int64(), ctypes.c_int64(), (ctypes.c_int * 4)()
+        _lib.check(self.lib.stb_launch_count(self.ctx, ctypes.byref(a), ctypes.byref(b), per))
+        return a.value, b.value, list(per)
+
     def set_targets(self, h, w, content_target, content_weight, means, srms, layer_weights, tv_weight, eps=1e-4):
         mp, _k1 = _lib.ptr_array(means)
         sp, _k2 = _lib.ptr_array(srms)
