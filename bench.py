@@ -109,8 +109,12 @@ class ClockSampler:
 def _use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core (the reference's CPU path does)."""
     import torch
-    n = os.cpu_count() or 1
-    if torch.get_num_threads() < n:
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or os.cpu_count() or 1   # physical cores: SMT siblings slow oneDNN down
+    except Exception:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() != n:
         torch.set_num_threads(n)
     return torch.get_num_threads()
 

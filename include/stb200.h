@@ -106,6 +106,19 @@ STB_API int stb_adam_update(float* img, const float* grad, float* exp_avg, float
                             int row0, int rows, int64_t step, float lr, float beta1, float beta2, float adam_eps,
                             float ema_decay, void* stream);
 
+/* ------------------------------------------------------------------ sync-free loss read-back (ST:487-493)
+ * host_ring: PINNED host memory, slots x 16 floats (NULL switches it off).  Each updating iteration stores its eight
+ * terms into slot (step % slots) and then the step as the slot's int32 stamp (word 8), from the loss kernel itself,
+ * BEFORE the backward pass starts: the host polls the stamp -- the per-iteration callback needs no stream sync and
+ * overlaps the rest of the iteration. */
+STB_API int stb_set_loss_ring(stb_ctx* ctx, float* host_ring, int slots);
+
+/* ------------------------------------------------------------------ per-scale warm start (ST:285-295, 420)
+ * out[1,C,Ho,Wo] = F.interpolate(in[1,C,H,W], (Ho,Wo), mode, align_corners=False) on the device, fp32.
+ * mode: 0 bilinear, 1 bicubic (A = -0.75).  post: 0 none, 1 relu (exp_avg_sq, ST:293), 2 clamp to [0,1] (image). */
+STB_API int stb_resize(const float* in, int C, int H, int W, float* out, int Ho, int Wo, int mode, int post,
+                       void* stream);
+
 /* ------------------------------------------------------------------ tiled iteration, exchanges inside the library
  * (csrc/comm.cu).  Each rank owns a MAILBOX (iteration stamps, its statistics block, its image gradient, its first /
  * last 80 updated rows) that the peers map with CUDA IPC and read over NVLink; stb_iterate_banded is then the whole

@@ -118,6 +118,9 @@ struct stb_ctx {
   bool graphs_enabled = true;
   std::string graph_note;  // why graph replay was switched off for this context (stb_graph_status)
   long long graph_replays = 0, kernels_replayed = 0;   // stb_launch_count
+  // sync-free loss read-back (stb_set_loss_ring): pinned host ring written by the finalize kernel itself
+  float* ring_dev = nullptr;   // device alias of the pinned host ring
+  int ring_slots = 0;
   bool band_on = false;
   int band_H_global = 0, band_own0 = 0, band_own_rows = 0;
   // peer-memory exchange of the tiled iteration (comm.cu)
@@ -330,9 +333,13 @@ __global__ void scale_copy_kernel(const float* __restrict__ in, float* __restric
 }
 
 // loss = cw * sse / numel + sum_l style_l + tvw * tv   (python sum, left to right, ST:208/455)
+// `ring` (optional): pinned HOST memory, slots x 16 floats.  The kernel stores the eight terms into slot
+// (step % slots) and then, after a system-scope fence, the step itself as the slot's stamp (word 8): the host polls the
+// stamp instead of synchronising the stream, so the callback of iteration i overlaps the backward pass of iteration i.
 __global__ void finalize_loss_kernel(const float* __restrict__ scalars, float content_scale,
                                      const float* __restrict__ style_terms, float tv_weight,
-                                     float* __restrict__ out) {
+                                     float* __restrict__ out, float* ring, int ring_slots,
+                                     const long long* __restrict__ d_step) {
   if (threadIdx.x == 0) {
     const float content = scalars[0] * content_scale;
     const float tv = scalars[1] * tv_weight;
@@ -343,6 +350,13 @@ __global__ void finalize_loss_kernel(const float* __restrict__ scalars, float co
     out[1] = content;
     for (int l = 0; l < 5; ++l) out[2 + l] = style_terms[l];
     out[7] = tv;
+    if (ring != nullptr && d_step != nullptr) {
+      const long long step = *d_step;
+      volatile float* slot = ring + (size_t)(step % ring_slots) * 16;
+      for (int i = 0; i < 8; ++i) slot[i] = out[i];
+      __threadfence_system();
+      reinterpret_cast<volatile int*>(slot)[8] = (int)step;
+    }
   }
 }
 
@@ -569,6 +583,16 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
   ctx->prof.begin(PC_W2, s);
   STB_TRY(ctx->w2.forward_backward(loss_dev + 16, s));
   ctx->prof.end(s);
+  // every loss term is known here (content SSE and TV from the forward, the style terms from the W2 forward): assemble
+  // and publish the loss BEFORE the backward pass, so a host callback can consume it while the device works on
+  ctx->prof.begin(PC_FINALIZE, s);
+  finalize_loss_kernel<<<1, 32, 0, s>>>(at<float>(ctx, pl.stats_off) + pl.stats_scalars,
+                                        ctx->content_weight / (float)n22, loss_dev + 16, ctx->tv_weight, loss_dev,
+                                        apply_update || ctx->band_on ? ctx->ring_dev : nullptr, ctx->ring_slots,
+                                        ctx->d_step);
+  ctx->prof.end(s);
+  if (loss_out_host8)
+    STB_CUDA_CHECK(cudaMemcpyAsync(loss_out_host8, loss_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
 
   bf16* g[2] = {at<bf16>(ctx, pl.g_off[0]), at<bf16>(ctx, pl.g_off[1])};
   int cur = 0;
@@ -632,13 +656,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
   STB_TRY(launch_conv0_bwd_adam(g[cur], true, ctx->w0, at<float>(ctx, pl.gtv_off), img, exp_avg, exp_avg_sq, ema,
                                 grad_out, H, W, d_adam, apply_update, s));
   ctx->prof.end(s);
-  ctx->prof.begin(PC_FINALIZE, s);
-  finalize_loss_kernel<<<1, 32, 0, s>>>(at<float>(ctx, pl.stats_off) + pl.stats_scalars,
-                                        ctx->content_weight / (float)n22, loss_dev + 16, ctx->tv_weight, loss_dev);
-  ctx->prof.end(s);
   STB_CUDA_CHECK(cudaGetLastError());
-  if (loss_out_host8)
-    STB_CUDA_CHECK(cudaMemcpyAsync(loss_out_host8, loss_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
   return STB_OK;
 }
 
@@ -802,6 +820,13 @@ int stb_adam_update(float* img, const float* grad, float* exp_avg, float* exp_av
                                                                                   W, row0, rows, as);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
+}
+
+// Per-scale warm start on the device: F.interpolate(in[1,C,H,W], (Ho,Wo), mode, align_corners=
+// False) of the image (bicubic, clamp; ST:420) and of the Adam moments (exp_avg bicubic, exp_avg_sq bilinear + relu;
+// ST:285-295).  mode: 0 bilinear, 1 bicubic; post: 0 none, 1 relu, 2 clamp to [0,1].
+int stb_resize(const float* in, int C, int H, int W, float* out, int Ho, int Wo, int mode, int post, void* stream) {
+  return launch_resize(in, C, H, W, out, Ho, Wo, mode, post, static_cast<cudaStream_t>(stream));
 }
 
 int stb_iterate(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step, float lr,
@@ -1011,6 +1036,23 @@ int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_
   key.H = pl.H; key.W = pl.W; key.ws = ctx->ws; key.img = img; key.m = exp_avg; key.v = exp_avg_sq; key.ema = ema;
   key.loss = loss_out_host8; key.lr = lr; key.b1 = beta1; key.b2 = beta2; key.eps = adam_eps; key.decay = ema_decay;
   return run_graphed(ctx, 3, key, true, s, run);
+}
+
+// Sync-free loss read-back.  host_ring: PINNED host memory of slots x 16 floats (NULL: off).
+// Every updating iteration then stores {loss, content, style1..5, tv} into slot (step % slots) and finally the step as
+// the slot's int32 stamp (word 8) -- written by the loss kernel itself right after the W2 forward, i.e. before the
+// backward pass: the host polls the stamp, no stream synchronisation.
+int stb_set_loss_ring(stb_ctx* ctx, float* host_ring, int slots) {
+  STB_ENTER(ctx);
+  ctx->reset_graphs();
+  ctx->ring_dev = nullptr; ctx->ring_slots = 0;
+  if (host_ring == nullptr) return STB_OK;
+  STB_CHECK(slots >= 2, STB_ERR_INVALID, "loss ring needs at least 2 slots");
+  void* dptr = nullptr;
+  STB_CUDA_CHECK(cudaHostGetDevicePointer(&dptr, host_ring, 0));
+  ctx->ring_dev = static_cast<float*>(dptr);
+  ctx->ring_slots = slots;
+  return STB_OK;
 }
 
 // 1: iterations replay as CUDA graphs; 0: eager launches (why: stb_last_error-style text in note_out, optional)

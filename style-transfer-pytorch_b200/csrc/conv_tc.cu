@@ -29,14 +29,18 @@ constexpr int TILE_H = 16, TILE_W = 8;           // output pixels per sub-tile =
 constexpr int A_ROWS = TILE_H + 2;               // dx buffer rows (halo above/below)
 constexpr int STG_BYTES = TILE_H * 1024;         // 128 pixels x 64 ch bf16 staging for the TMA store
 constexpr int PSTG_BYTES = (TILE_H / 2) * (TILE_W / 2) * 128;
-constexpr int NUM_EPI_THREADS = 128;
-constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
+constexpr int NUM_EPI_THREADS = 128;   // one epilogue group = 4 warps = the 128 TMEM lanes
 
 // MT = horizontally adjacent 16x8 sub-tiles per CTA tile that share every weight stage (halves the L2->smem
 // weight traffic per MMA for the narrow-N layers, which are L2-bandwidth bound otherwise).
 template <int BN>
 struct Cfg {
   static constexpr int MT = BN == 256 ? 1 : 2;
+  // Epilogue groups.  With N = 64 a sub-tile's MMAs last ~1150 cycles (36 x 32), less than its epilogue (TMEM load,
+  // mask / pool reads, bf16 pack, swizzled staging, TMA store): the C = 64 layers were epilogue-paced (37-50 % tensor
+  // pipe in round 1).  They get TWO groups of four warps, one per sub-tile, each with its own staging buffer.
+  static constexpr int EG = BN == 64 ? 2 : 1;
+  static constexpr int NUM_THREADS = 64 + EG * NUM_EPI_THREADS;
   static constexpr int NA = 3;
   static constexpr int NB = BN == 64 ? 8 : 4;
   static constexpr int A_PITCH = MT * 1024;                 // bytes per row of 8*MT pixels
@@ -69,7 +73,7 @@ struct KParams {
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<BN>::NUM_THREADS, 1)
 pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool,
@@ -103,7 +107,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmPool);
     for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * C::EG); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
@@ -116,7 +120,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // produced by the W2 chain) are read only from here on.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  for (int i = threadIdx.x; i < p.Cout && i < 512; i += NUM_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.Cout && i < 512; i += C::NUM_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   __syncthreads();
 
   if (warp == 0) {
@@ -227,13 +231,16 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   } else {
-    // =============================================================== epilogue (4 warps, TMEM lane group = warp % 4)
+    // =============================================================== epilogue (4 warps per group, TMEM lane group =
+    // warp % 4; EG groups split the sub-tiles of a CTA tile between them)
     const int wq = warp & 3;
     const int r = wq * 32 + lane;         // row of the tile = TMEM lane = pixel
-    const int et = threadIdx.x - 64;      // 0..127
+    const int grp = (threadIdx.x - 64) / NUM_EPI_THREADS;
+    const int et = (threadIdx.x - 64) % NUM_EPI_THREADS;      // 0..127 inside the group
+    const uint32_t bar0 = 1 + 3 * grp;    // named barriers of this group
     int acc = 0;
     uint32_t pacc = 0;
-    int stg = 0;
+    int stg = C::EG == 2 ? grp : 0;       // two groups: each owns one staging buffer
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int tn = tile % p.n_tiles_n;
       const int t2 = tile / p.n_tiles_n;
@@ -242,7 +249,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int mj = 0; mj < C::MT * (BN / 64); ++mj) {
+      for (int mj = (C::EG == 2 ? grp : 0); mj < C::MT * (BN / 64); mj += C::EG) {
         const int m = mj / (BN / 64), j = mj % (BN / 64);
         const int x0 = (tx * C::MT + m) * TILE_W;
         const int py = y0 + (r >> 3), px = x0 + (r & 7);
@@ -252,8 +259,11 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + (acc * C::MT + m) * BN;
         uint8_t* stage = smem + C::OFF_STG + stg * STG_BYTES;
         // make sure the TMA store that last read this staging buffer is done, then let everyone write
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        named_bar_sync(1, NUM_EPI_THREADS);
+        if (et == 0) {
+          if (C::EG == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // single buffer per group
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        named_bar_sync(bar0, NUM_EPI_THREADS);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -317,7 +327,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, NUM_EPI_THREADS);
+        named_bar_sync(bar0 + 1, NUM_EPI_THREADS);
         const bool pooled = (MODE == 0) && p.pooling >= 0;
         if (et == 0) {
           tma_store_3d(&tmOut, stage, n0 + j * 64, x0, y0);
@@ -363,13 +373,13 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             *reinterpret_cast<uint4*>(pst + pp * 128 + ((c16 ^ (pp & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(3, NUM_EPI_THREADS);
+          named_bar_sync(bar0 + 2, NUM_EPI_THREADS);
           if (et == 0) {
             tma_store_3d(&tmPool, pst, n0 + j * 64, x0 >> 1, y0 >> 1);
             tma_store_commit();
           }
         }
-        stg ^= 1;
+        if (C::EG == 1) stg ^= 1;
       }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -398,7 +408,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   static const bool pdl = [] { const char* e = getenv("STB_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];

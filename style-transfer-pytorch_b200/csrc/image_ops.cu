@@ -422,12 +422,78 @@ int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int
   return STB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ per-scale resize
+// F.interpolate(x, (Ho, Wo), mode='bicubic' | 'bilinear') with align_corners=False, antialias=False, as the reference
+// uses it for the warm start of a scale: image bicubic + clamp (ST:420), Adam exp_avg bicubic, exp_avg_sq bilinear +
+// relu (ST:285-295).  Restates ATen's upsample_bicubic2d / upsample_bilinear2d (UpSample.h: cubic convolution with
+// A = -0.75, source index scale * (dst + 0.5) - 0.5, bounded reads; bilinear clamps the source index at 0).
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+// mode: 0 bilinear, 1 bicubic; post: 0 none, 1 relu, 2 clamp to [0, 1]
+__global__ void __launch_bounds__(256)
+resize_kernel(const float* __restrict__ in, int C, int H, int W, float* __restrict__ out, int Ho, int Wo, float sh,
+              float sw, int mode, int post) {
+  const long total = (long)C * Ho * Wo;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % Wo);
+    const long t2 = i / Wo;
+    const int yo = (int)(t2 % Ho), c = (int)(t2 / Ho);
+    const float* __restrict__ pl = in + (size_t)c * H * W;
+    float v;
+    if (mode == 1) {
+      const float ry = sh * (yo + 0.5f) - 0.5f, rx = sw * (xo + 0.5f) - 0.5f;
+      const float fy = floorf(ry), fx = floorf(rx);
+      const int iy = (int)fy, ix = (int)fx;
+      float wy[4], wx[4];
+      cubic_coeffs(ry - fy, wy);
+      cubic_coeffs(rx - fx, wx);
+      v = 0.f;
+      float rows[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float* __restrict__ row = pl + (size_t)clampi(iy - 1 + a, 0, H - 1) * W;
+        // ATen: cubic_interp1d(x0, x1, x2, x3, t) = x0*c0 + x1*c1 + x2*c2 + x3*c3, rows first, then columns
+        rows[a] = __ldg(row + clampi(ix - 1, 0, W - 1)) * wx[0] + __ldg(row + clampi(ix, 0, W - 1)) * wx[1] +
+                  __ldg(row + clampi(ix + 1, 0, W - 1)) * wx[2] + __ldg(row + clampi(ix + 2, 0, W - 1)) * wx[3];
+      }
+      v = rows[0] * wy[0] + rows[1] * wy[1] + rows[2] * wy[2] + rows[3] * wy[3];
+    } else {
+      const float ry = fmaxf(sh * (yo + 0.5f) - 0.5f, 0.f), rx = fmaxf(sw * (xo + 0.5f) - 0.5f, 0.f);
+      const int y0 = (int)ry, x0 = (int)rx;
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float ly = ry - y0, lx = rx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      v = hy * (hx * __ldg(pl + (size_t)y0 * W + x0) + lx * __ldg(pl + (size_t)y0 * W + x1)) +
+          ly * (hx * __ldg(pl + (size_t)y1 * W + x0) + lx * __ldg(pl + (size_t)y1 * W + x1));
+    }
+    if (post == 1) v = fmaxf(v, 0.f);
+    else if (post == 2) v = fminf(fmaxf(v, 0.f), 1.f);
+    out[i] = v;
+  }
+}
+
+int launch_resize(const float* in, int C, int H, int W, float* out, int Ho, int Wo, int mode, int post, cudaStream_t s) {
+  STB_CHECK(in && out && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, STB_ERR_INVALID, "resize: bad shape");
+  STB_CHECK((mode == 0 || mode == 1) && post >= 0 && post <= 2, STB_ERR_INVALID, "resize: mode=%d post=%d", mode, post);
+  // ATen area_pixel_compute_scale with align_corners=False and no explicit scale_factor: input / output, in float
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  resize_kernel<<<grid_for((long)C * Ho * Wo, 256), 256, 0, s>>>(in, C, H, W, out, Ho, Wo, sh, sw, mode, post);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
 int preload_image_kernels() {
   cudaFuncAttributes fa;
 #define STB_PRELOAD(k) STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)))
   STB_PRELOAD(tv_kernel); STB_PRELOAD(pack_w0_fwd_kernel); STB_PRELOAD(conv0_bwd_adam_kernel);
   STB_PRELOAD(pool_bwd_kernel<STB_POOL_MAX>); STB_PRELOAD(pool_bwd_kernel<STB_POOL_AVERAGE>);
-  STB_PRELOAD(pool_bwd_kernel<STB_POOL_L2>); STB_PRELOAD(sse_kernel);
+  STB_PRELOAD(pool_bwd_kernel<STB_POOL_L2>); STB_PRELOAD(sse_kernel); STB_PRELOAD(resize_kernel);
 #undef STB_PRELOAD
   return STB_OK;
 }

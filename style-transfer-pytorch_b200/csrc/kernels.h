@@ -69,6 +69,9 @@ int launch_conv0_bwd_interior(const bf16* g0, const bf16* w0q, const float* gtv,
                               int apply_update, cudaStream_t s);
 int launch_pool_bwd(int pooling, const bf16* gout, const bf16* y, bf16* gin, int H, int W, int C, cudaStream_t s);
 int launch_sse(const bf16* a, const bf16* b, long n, float* partials, int* n_partials, cudaStream_t s);
+// F.interpolate(align_corners=False) on fp32 [C][H][W] planes: mode 0 bilinear / 1 bicubic; post 0 none / 1 relu /
+// 2 clamp to [0,1]  (warm start of a scale, ST:285-295, 420)
+int launch_resize(const float* in, int C, int H, int W, float* out, int Ho, int Wo, int mode, int post, cudaStream_t s);
 
 // ---------------------------------------------------------------- Gram / channel sums on tcgen05 (gram_tc.cu)
 int gram_num_splits(long P, int C);

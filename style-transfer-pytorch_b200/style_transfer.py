@@ -18,7 +18,6 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 from PIL import Image
-from torch.nn import functional as F
 
 from . import _lib
 from . import distributed as D
@@ -59,12 +58,6 @@ def gen_scales(start, end):
         i += 1
         scale = round(end / pow(2, i / 2))
     return sorted(out)
-
-
-def _resize(x, hw, mode):
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore', UserWarning)
-        return F.interpolate(x, hw, mode=mode)
 
 
 def _pil_to_tensor(img, device=None):
@@ -250,6 +243,17 @@ class NativeVGG:
         note = ctypes.create_string_buffer(512)
         return self.lib.stb_graph_status(self.ctx, note, 512), note.value.decode(errors='replace')
 
+    def resize(self, x, hw, mode, post=None):
+        """F.interpolate(x, hw, mode=mode, align_corners=False) on the device by the library's own kernel
+        (stb_resize): the warm start of a scale, ST:285-295 / ST:420.  post: None | 'relu' | 'clamp'."""
+        x = x.detach().to(self.device, torch.float32).contiguous()
+        n, c, h, w = x.shape
+        out = torch.empty(n, c, hw[0], hw[1], dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.stb_resize(_lib.ptr(x), n * c, h, w, _lib.ptr(out), hw[0], hw[1],
+                                       {'bilinear': 0, 'bicubic': 1}[mode], {None: 0, 'relu': 1, 'clamp': 2}[post],
+                                       _lib.cur_stream()))
+        return out
+
     def launch_count(self):
         """(graph replays, kernels launched by them, kernel nodes per graph slot) -- counted from the captured graphs."""
         a, b, per = ctypes.c_int64(), ctypes.c_int64(), (ctypes.c_int * 4)()
@@ -265,6 +269,8 @@ class NativeVGG:
 
 
 class StyleTransfer:
+    RING_SLOTS = 8
+
     def __init__(self, devices=['cpu'], pooling='max', *, vgg_weights=None, distributed=None):
         self.devices = [torch.device(device) for device in devices]
         self.image = None
@@ -299,6 +305,13 @@ class StyleTransfer:
             vgg_weights = load_vgg19_conv_weights()
         self.model = NativeVGG(vgg_weights, pooling, dev)
         self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # sync-free loss read-back (stb_set_loss_ring): the loss kernel itself writes the terms + an iteration stamp
+        # into this pinned ring before the backward pass starts; the callback path polls the stamp
+        self._ring = torch.zeros(self.RING_SLOTS, 16, dtype=torch.float32).pin_memory()
+        self._ring_f32 = self._ring.numpy()
+        self._ring_i32 = self._ring_f32.view(np.int32)
+        with torch.cuda.device(dev):
+            _lib.check(self.model.lib.stb_set_loss_ring(self.model.ctx, _lib.ptr(self._ring), self.RING_SLOTS))
         # iterations run on a dedicated (non-legacy) stream so that the library can replay them as a CUDA graph
         self._stream = torch.cuda.Stream(device=dev)
         self.last_loss_terms = None
@@ -457,6 +470,20 @@ class StyleTransfer:
         srms = [t / n for t, n in zip(out[5:], counts)]
         return means, srms
 
+    def _wait_loss(self, step):
+        """Loss terms of iteration `step` as soon as the device has published them (before its backward pass): polls the
+        stamp of the ring slot in pinned host memory -- no stream synchronisation, the rest of the iteration and the
+        launch of the next one overlap the callback."""
+        slot = step % self.RING_SLOTS
+        stamp = self._ring_i32[slot]
+        t0 = None
+        while stamp[8] != step:
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > 120.0:
+                raise _lib.NativeError(f'iteration {step}: the device never published its loss (stamp {int(stamp[8])})')
+        return torch.from_numpy(self._ring_f32[slot, :8].copy())
+
     def loss_and_grad(self):
         """Closure of ST:472-476 evaluated natively on the current image: returns (terms[8] host tensor, grad)."""
         m = self.model
@@ -537,7 +564,7 @@ class StyleTransfer:
                     style_sizes.append((sb.h_local if sb is not None else sh, sw))
                 self.model.ensure_workspace([(h_loc, cw)] + style_sizes)
 
-                self.image = _resize(self.image.detach(), (ch, cw), 'bicubic').clamp_(0, 1).contiguous()
+                self.image = self.model.resize(self.image, (ch, cw), 'bicubic', 'clamp')          # ST:420
                 if band is not None:
                     full_image = self.image
                     self.image = D.local_slice(full_image, band)
@@ -574,8 +601,8 @@ class StyleTransfer:
                         exp_avg = torch.zeros_like(self.image)
                         exp_avg_sq = torch.zeros_like(self.image)
                     else:  # warm start at the new size, step counter carried over (ST:285-295, 460-462)
-                        exp_avg = _resize(exp_avg, (ch, cw), 'bicubic').contiguous()
-                        exp_avg_sq = _resize(exp_avg_sq, (ch, cw), 'bilinear').relu_().contiguous()
+                        exp_avg = self.model.resize(exp_avg, (ch, cw), 'bicubic')
+                        exp_avg_sq = self.model.resize(exp_avg_sq, (ch, cw), 'bilinear', 'relu')
                     if band is not None:
                         if exp_avg.shape[2] != h_loc:
                             exp_avg, exp_avg_sq = D.local_slice(exp_avg, band), D.local_slice(exp_avg_sq, band)
@@ -605,9 +632,12 @@ class StyleTransfer:
                             if device.type == 'cuda':
                                 gpu_ram = max(gpu_ram, torch.cuda.max_memory_allocated(device))
                         if optimizer == 'adam':
-                            torch.cuda.current_stream().synchronize()   # the reference syncs here too (loss.item())
-                            self.last_loss_terms = self._loss_host.clone()
-                            loss_value = float(self._loss_host[0])
+                            if band is not None and self._comm_mode != 'peer':
+                                torch.cuda.current_stream().synchronize()   # host-driven exchanges: plain read-back
+                                self.last_loss_terms = self._loss_host.clone()
+                            else:   # the reference syncs here (loss.item()); this waits for the loss only
+                                self.last_loss_terms = self._wait_loss(step)
+                            loss_value = float(self.last_loss_terms[0])
                         callback(STIterate(w=cw, h=ch, i=i, i_max=actual_its, loss=loss_value, time=time.time(),
                                            gpu_ram=gpu_ram))
 

@@ -225,3 +225,21 @@ def test_w2_loss_sqrtm_and_backward(G, C):
     assert abs(loss.item() - l.item()) / abs(l.item()) < 1e-3   # cancellation: fp32 vs fp64
     assert G.rel_err(gs, gsr) < 2e-3
     assert G.rel_err(gmu * npix, gmr) < 2e-3
+
+
+@pytest.mark.parametrize('C,H,W,Ho,Wo', [(3, 96, 128, 136, 181), (3, 181, 136, 256, 192), (3, 64, 64, 64, 64),
+                                         (3, 50, 70, 35, 49), (1, 17, 33, 24, 47)])
+def test_native_resize_matches_interpolate(G, C, H, W, Ho, Wo):
+    """stb_resize vs F.interpolate(align_corners=False) for the per-scale warm start (ST:285-295, 420): bicubic and
+    bilinear, with the relu / clamp epilogues; the CPU kernels of torch are the yardstick (1e-6: same formulas, fp32)."""
+    from style_transfer_b200 import _lib
+    g = torch.Generator().manual_seed(C * H + W)
+    x = torch.rand(1, C, H, W, generator=g) * 1.4 - 0.2
+    xd = x.to(G.DEV)
+    for mode, code in (('bilinear', 0), ('bicubic', 1)):
+        want = F.interpolate(x, (Ho, Wo), mode=mode, align_corners=False)
+        for post, fn in ((0, lambda t: t), (1, torch.relu), (2, lambda t: t.clamp(0, 1))):
+            out = torch.empty(1, C, Ho, Wo, device=G.DEV)
+            _lib.check(_lib.load().stb_resize(_lib.ptr(xd), C, H, W, _lib.ptr(out), Ho, Wo, code, post, _lib.cur_stream()))
+            torch.cuda.synchronize()
+            assert (out.cpu() - fn(want)).abs().max().item() < 2e-6, (mode, post)

