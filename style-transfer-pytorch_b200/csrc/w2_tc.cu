@@ -272,9 +272,20 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red) {
   for (int i = 0; i < 8; ++i) t += s_red[i];
   return t;
 }
-__device__ __forceinline__ void sum_partials(const float* red, int count, float& a, float& b) {
+// Sum of the (<= NRED) reduction partials {a_i, b_i}, by the whole 256-thread block in a fixed tree (every CTA of a
+// layer gets the same bits).  Was a serial loop in every thread: 32-128 dependent-issue global loads at the head of
+// each element-wise helper, ~20 us of the 40-50 us those kernels took.
+__device__ __forceinline__ void sum_partials(const float* red, int count, float& a, float& b, float* s_red16) {
+  float va = 0.f, vb = 0.f;
+  if ((int)threadIdx.x < count) { va = red[2 * threadIdx.x]; vb = red[2 * threadIdx.x + 1]; }
+  va = warp_sum(va);
+  vb = warp_sum(vb);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_red16[threadIdx.x >> 5] = va; s_red16[8 + (threadIdx.x >> 5)] = vb; }
+  __syncthreads();
   a = 0.f; b = 0.f;
-  for (int i = 0; i < count; ++i) { a += red[2 * i]; b += red[2 * i + 1]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a += s_red16[i]; b += s_red16[8 + i]; }
 }
 __device__ __forceinline__ int gemm_tiles(int n) { return ((n + TM - 1) / TM) * (n / TN); }
 
@@ -323,12 +334,13 @@ __global__ void __launch_bounds__(256) w2_cov_kernel(const W2Layer* __restrict__
 
 // Y = M / ||M||_F, Z = I        (SQ:15-19).  ||M||^2 arrives as partials (cov kernel: NB; GEMM tiles otherwise)
 __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restrict__ layers, int from_target) {
+  __shared__ float s_red16[16];
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   const float* M = from_target ? L.cov_t : L.M;
   float ss, dummy;
-  sum_partials(L.red, from_target ? NB : gemm_tiles(n), ss, dummy);
+  sum_partials(L.red, from_target ? NB : gemm_tiles(n), ss, dummy, s_red16);
   const float norm = sqrtf(ss);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
@@ -355,11 +367,12 @@ __global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __
 // forward finish: R = Y sqrt(normA); loss; seeds of the Lyapunov backward    (SQ:25, ST:178-181, SQ:37-41).
 // ||Y||^2 and tr(Y) arrive as per-tile partials written by the last NS round.
 __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __restrict__ layers, float* loss_terms) {
+  __shared__ float s_red16[16];
   const W2Layer L = layers[blockIdx.x];
   const int n = L.n;
   const size_t nn = (size_t)n * n;
   float ss, tr;
-  sum_partials(L.red, gemm_tiles(n), ss, tr);
+  sum_partials(L.red, gemm_tiles(n), ss, tr, s_red16);
   const float sq = sqrtf(L.scal[W2S_NORM_A]);
   const float norm_y = sqrtf(ss);
   const float norm_r = sq * norm_y;                     // ||R||_F

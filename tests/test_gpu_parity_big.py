@@ -33,7 +33,13 @@ LOSS_TOL = 1e-3          # north_star
 # 256^2, where accumulation length plays no role).  The content MSE is a small difference of two independently rounded
 # bf16 feature maps: the rounding noise adds its variance to it (0.7e-3 at 256^2 ... 5.8e-3 at 4096^2 of a term that
 # is 1.5-3.5 % of the loss).  TV is fp32 on the raw image.
-TERM_TOL = dict(content=8e-3, relu1_1=1e-3, relu2_1=1e-3, relu3_1=2e-3, relu4_1=3e-3, relu5_1=3.5e-3, tv=1e-5)
+TERM_TOL = dict(content=8e-3, relu1_1=1e-3, relu2_1=1e-3, relu3_1=2.5e-3, relu4_1=3e-3, relu5_1=3.5e-3, tv=1e-5)
+# ... and that gap IS the operand quantisation BASELINE.json configs[2] prescribes ("bf16 conv / fp32 accumulate"): the
+# fixtures also hold the same case evaluated by the oracle's `sim_bf16` mode (reference algorithm + bf16-rounded conv
+# weights + bf16-stored activations / feature gradients, nothing else changed; tests/golden/make_big_parity.py sim).
+# Against THAT every native term must agree to a few 1e-4 -- a kernel bug cannot hide behind the bf16 allowance.
+SIM_TERM_TOL = dict(content=1.5e-3, relu1_1=4e-4, relu2_1=4e-4, relu3_1=6e-4, relu4_1=6e-4, relu5_1=8e-4, tv=1e-5)
+SIM_LOSS_TOL = 4e-4
 RECORD = Path(__file__).resolve().parent.parent / 'gpurun_out'
 
 
@@ -79,6 +85,10 @@ def test_loss_terms_and_gradient_match_the_reference(G, vgg_weights, size):
     rec = dict(size=size, total=float(terms[0]), total_ref=float(gold['total']), total_rel_err=float(total_err),
                term_rel_err=dict(zip(TERM_NAMES, map(float, term_err))), grad_norm_rel_err=float(norm_err),
                grad_cos_block_means=cos_pooled, grad_cos_crop=cos_crop)
+    if 'terms_sim' in gold.files:
+        sim_err = np.abs(terms[1:8] - gold['terms_sim']) / np.abs(gold['terms_sim'])
+        rec['vs_sim_bf16_oracle'] = dict(total=float(abs(terms[0] - gold['total_sim']) / gold['total_sim']),
+                                         terms=dict(zip(TERM_NAMES, map(float, sim_err))))
     print(json.dumps(rec))
     if RECORD.is_dir():
         with open(RECORD / 'parity_big.jsonl', 'a') as f:
@@ -86,6 +96,10 @@ def test_loss_terms_and_gradient_match_the_reference(G, vgg_weights, size):
     assert total_err < LOSS_TOL, rec
     for name, e in zip(TERM_NAMES, term_err):
         assert e < TERM_TOL[name], (name, rec)
+    if 'terms_sim' in gold.files:
+        assert rec['vs_sim_bf16_oracle']['total'] < SIM_LOSS_TOL, rec
+        for name, e in zip(TERM_NAMES, sim_err):
+            assert e < SIM_TERM_TOL[name], (name, rec)
     # gradient: bf16 activations / feature gradients move individual pixels by a few %, not the direction
     assert norm_err < 2e-2, rec
     assert cos_pooled > 0.999 and cos_crop > 0.995, rec
