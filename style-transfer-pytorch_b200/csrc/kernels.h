@@ -94,7 +94,7 @@ struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major; a matrix
   int write_t;  // also write the planes of D^T (D is later used as a right factor)
 };
 constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152;
-struct W2Round {  // one grouped launch; travels as a __grid_constant__ kernel parameter (no dependent global loads)
+struct W2Round {  // one grouped GEMM step of all layers; lives in device memory, walked by w2_chain_kernel
   int n_tiles, n_probs;
   TcProb probs[W2_MAX_PROBS];
   uint32_t tiles[W2_MAX_TILES];  // prob << 16 | tile row << 8 | tile col
@@ -119,6 +119,8 @@ struct W2Engine {
   W2Layer host_layers[5];
   W2Layer* d_layers = nullptr;
   CUtensorMap* d_maps = nullptr;
+  W2Round* d_rounds = nullptr;        // device copy of `rounds` (the chain kernel walks it)
+  unsigned* d_grid_counter = nullptr; // grid barrier of the chain kernel (zeroed before every launch)
   std::vector<W2Round> rounds;
   int r_target_begin = 0, r_target_end = 0, r_fwd_begin = 0, r_fwd_ns_begin = 0, r_fwd_end = 0, r_bwd_begin = 0,
       r_bwd_end = 0, gc_round = 0;

@@ -85,7 +85,18 @@ __device__ __forceinline__ float load2(const float* m, size_t nn, size_t e) { re
 constexpr int STG_OFF = 0;                          // 4 store tiles (2 column halves x hi/lo) of 16 KiB, SW128, in
 static_assert(4 * A_PLANE_BYTES <= T_STAGES * T_STAGE_BYTES, "epilogue smem");  // the drained pipeline buffers
 
-__global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_constant__ W2Round rp) {
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The whole chain of rounds [r0, r1) in ONE persistent, cooperatively launched kernel: one CTA per SM, tile t of a
+// round goes to CTA t % gridDim.x, a grid-wide barrier separates two rounds.  Replaces 24-26 dependent launches per
+// phase: barrier init, TMEM allocation and the launch / drain latency of a grid are paid once, a round boundary costs
+// one atomic + one acquire spin (~1.5 us instead of ~4 us of launch gap).  The arithmetic of a tile is unchanged.
+__global__ void __launch_bounds__(T_THREADS, 1)
+w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __restrict__ grid_counter) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + T_OFF_BAR);
@@ -93,21 +104,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
   uint64_t* t_full = empty + T_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + T_OFF_TMEMPTR);
   float* s_red = reinterpret_cast<float*>(smem + T_OFF_RED);
-
-  const uint32_t t = rp.tiles[blockIdx.x];
-  const TcProb& pr = rp.probs[t >> 16];
-  const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
-  const int n = pr.n;
-  const int n_k = n / TKF;
-  const int steps_per_acc = (n / 8 + T_MAX_ACC - 1) / T_MAX_ACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < T_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(t_full, 1);
     fence_barrier_init();
-    tma_prefetch_desc(pr.amap); tma_prefetch_desc(pr.amap + 1);
-    tma_prefetch_desc(pr.bmap); tma_prefetch_desc(pr.bmap + 1);
   }
   if (warp == 1) tmem_alloc<T_TMEM_COLS>(tmem_ptr);
   tc_fence_before();
@@ -115,146 +117,201 @@ __global__ void __launch_bounds__(T_THREADS, 1) w2_gemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // Programmatic dependent launch: the rounds are a chain of 52 dependent grids of <= 98 CTAs on 148 SMs.  Everything
-  // above (barrier init, TMEM allocation, descriptor prefetch) ran on idle SMs while the previous round was still
-  // computing; only from here on are its results touched.  Releasing our own dependents right after the wait keeps
-  // the run-ahead at exactly one round.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // pipeline ring state, persistent across tiles and rounds (the producer and the MMA warp advance identically)
+  int s = 0;
+  uint32_t ph = 0, tile_parity = 0;
+  unsigned barriers_done = 0;
 
-  if (warp == 0) {
-    // ---- TMA producer: four planes per stage
-    if (elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int k = 0; k < n_k; ++k) {
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], T_STAGE_BYTES);
-        uint8_t* st = smem + s * T_STAGE_BYTES;
-        tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
-        tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
-        tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
-        tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
-        if (++s == T_STAGES) { s = 0; ph ^= 1; }
+  // The tile -> CTA map is static, so everything a CTA needs for its first tile of the NEXT round (problem record,
+  // tensor-map descriptors) is fetched BEFORE the grid barrier: after it the producer can issue its TMA loads at once
+  // instead of first walking rounds[] -> tiles[] -> probs[] -> descriptor through dependent L2 reads.
+  uint32_t pre_t = 0;
+  int pre_n_tiles = 0;
+  TcProb pre_pr = {};
+  auto prefetch_round = [&](int round) {
+    const W2Round& nx = rounds[round];
+    pre_n_tiles = nx.n_tiles;
+    if ((int)blockIdx.x < pre_n_tiles) {
+      pre_t = nx.tiles[blockIdx.x];
+      pre_pr = nx.probs[pre_t >> 16];
+      if (threadIdx.x == 0) {
+        tma_prefetch_desc(pre_pr.amap); tma_prefetch_desc(pre_pr.amap + 1);
+        tma_prefetch_desc(pre_pr.bmap); tma_prefetch_desc(pre_pr.bmap + 1);
+        tma_prefetch_desc(pre_pr.dmap); tma_prefetch_desc(pre_pr.dmap + 1);
       }
-      tma_prefetch_desc(pr.dmap); tma_prefetch_desc(pr.dmap + 1);
-      tma_prefetch_desc(pr.dmap + 2); tma_prefetch_desc(pr.dmap + 3);
     }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage.  The tensor core aligns every product to
-    // the accumulator and truncates, so a chain of m products loses ~2^-25 * m of the sum, systematically; on the
-    // ill-conditioned covariances of real activations the Newton-Schulz iteration turns that into a -1e-3 bias of the
-    // style terms (measured).  hi*hi therefore runs in short chains: the n/8 k-steps are dealt out in equal runs to
-    // seven TMEM accumulators (2 steps each at C = 64 ... 10 at C = 512), the small cross terms go to an eighth, and
-    // the epilogue adds all of them in round-to-nearest fp32.
-    constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
-    constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
-    const bool leader = elect_one();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int k = 0; k < n_k; ++k) {
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t base = smem_u32(smem + s * T_STAGE_BYTES);
-        const uint32_t a_h = umma_desc_lo(base), a_l = umma_desc_lo(base + A_PLANE_BYTES);
-        const uint32_t b_h = umma_desc_lo(base + 2 * A_PLANE_BYTES);
-        const uint32_t b_l = umma_desc_lo(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
-          const int step = k * (TKF / 8) + kk;
-          const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
-          umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
-          umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
-          umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
+  };
+  prefetch_round(r0);
+
+  for (int round = r0; round < r1; ++round) {
+    const W2Round& rp = rounds[round];
+    const int n_tiles = pre_n_tiles;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool first = tile == (int)blockIdx.x;
+      const uint32_t t = first ? pre_t : rp.tiles[tile];
+      const TcProb pr = first ? pre_pr : rp.probs[t >> 16];
+      const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
+      const int n = pr.n;
+      const int n_k = n / TKF;
+      const int steps_per_acc = (n / 8 + T_MAX_ACC - 1) / T_MAX_ACC;
+
+      if (warp == 0) {
+        // ---- TMA producer: four planes per stage
+        const bool leader = elect_one();   // every lane walks the ring state, the elected one issues
+        for (int k = 0; k < n_k; ++k) {
+          if (leader) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], T_STAGE_BYTES);
+            uint8_t* st = smem + s * T_STAGE_BYTES;
+            tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
+            tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
+            tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
+            tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
+          }
+          if (++s == T_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty[s]);
-      }
-      __syncwarp();
-      if (++s == T_STAGES) { s = 0; ph ^= 1; }
-    }
-    if (leader) umma_commit(t_full);
-    __syncwarp();
-  } else {
-    // ---- epilogue (128 threads, TMEM lane = tile row)
-    const int wq = warp & 3;
-    const int r = wq * 32 + lane;
-    const int gi = ti * TM + r;
-    const size_t nn = (size_t)n * n;
-    uint8_t* stg = smem + STG_OFF;
-    mbar_wait(t_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const int n_chunks = (n / 8 + steps_per_acc - 1) / steps_per_acc;
-    const bool valid = gi < n;
-    float ssq = 0.f, tr = 0.f;
+        __syncwarp();
+      } else if (warp == 1) {
+        // ---- MMA issuer: 4 k-steps (K = 8) x 3 split products per stage.  The tensor core aligns every product to
+        // the accumulator and truncates, so a chain of m products loses ~2^-25 * m of the sum, systematically; on the
+        // ill-conditioned covariances of real activations the Newton-Schulz iteration turns that into a -1e-3 bias of
+        // the style terms (measured).  hi*hi therefore runs in short chains: the n/8 k-steps are dealt out in equal
+        // runs to seven TMEM accumulators (2 steps each at C = 64 ... 10 at C = 512), the small cross terms go to an
+        // eighth, and the epilogue adds all of them in round-to-nearest fp32.
+        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+        constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
+        const bool leader = elect_one();
+        for (int k = 0; k < n_k; ++k) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t base = smem_u32(smem + s * T_STAGE_BYTES);
+            const uint32_t a_h = umma_desc_lo(base), a_l = umma_desc_lo(base + A_PLANE_BYTES);
+            const uint32_t b_h = umma_desc_lo(base + 2 * A_PLANE_BYTES);
+            const uint32_t b_l = umma_desc_lo(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
+              const int step = k * (TKF / 8) + kk;
+              const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+              umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
+              umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
+              umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
+            }
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
+          if (++s == T_STAGES) { s = 0; ph ^= 1; }
+        }
+        if (leader) umma_commit(t_full);
+        __syncwarp();
+      } else {
+        // ---- epilogue (128 threads, TMEM lane = tile row)
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        const int gi = ti * TM + r;
+        const size_t nn = (size_t)n * n;
+        uint8_t* stg = smem + STG_OFF;
+        mbar_wait(t_full, tile_parity);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+        const int n_chunks = (n / 8 + steps_per_acc - 1) / steps_per_acc;
+        const bool valid = gi < n;
+        float ssq = 0.f, tr = 0.f;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      uint32_t v[32];
-      float acc[32];
-      tmem_ld_32x32(taddr + h * 32, v);
-      tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          float acc[32];
+          tmem_ld_32x32(taddr + h * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
-      for (int c = 1; c < n_chunks; ++c) {
-        tmem_ld_32x32(taddr + c * TN + h * 32, v);
-        tmem_ld_wait();
+          for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
+          for (int c = 1; c < n_chunks; ++c) {
+            tmem_ld_32x32(taddr + c * TN + h * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
-      }
-      tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
-      tmem_ld_wait();
-      const int gj0 = tj * TN + h * 32;
-      uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
-      uint8_t* row_lo = row_hi + A_PLANE_BYTES;
+            for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
+          }
+          tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
+          tmem_ld_wait();
+          const int gj0 = tj * TN + h * 32;
+          uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
+          uint8_t* row_lo = row_hi + A_PLANE_BYTES;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float vh[4], vl[4];
+          for (int q = 0; q < 8; ++q) {
+            float vh[4], vl[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float o = (acc[4 * q + e] + __uint_as_float(v[4 * q + e])) * pr.alpha;
-          if (gi == gj0 + 4 * q + e) { o += pr.gamma; tr += o; }
-          if (valid) ssq = fmaf(o, o, ssq);
-          split_tf32(o, vh[e], vl[e]);
-        }
-        const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
-        *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-        *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
-        if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 B
+            for (int e = 0; e < 4; ++e) {
+              float o = (acc[4 * q + e] + __uint_as_float(v[4 * q + e])) * pr.alpha;
+              if (gi == gj0 + 4 * q + e) { o += pr.gamma; tr += o; }
+              if (valid) ssq = fmaf(o, o, ssq);
+              split_tf32(o, vh[e], vl[e]);
+            }
+            const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
+            *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+            *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+            if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 B
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const size_t at = 2 * nn + (size_t)(gj0 + 4 * q + e) * n + gi;
-            pr.D[at] = vh[e];
-            pr.D[nn + at] = vl[e];
+              for (int e = 0; e < 4; ++e) {
+                const size_t at = 2 * nn + (size_t)(gj0 + 4 * q + e) * n + gi;
+                pr.D[at] = vh[e];
+                pr.D[nn + at] = vl[e];
+              }
+            }
           }
         }
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (r == 0) {
-      const CUtensorMap* dm = pr.dmap;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        // the D^T planes were written through the generic proxy; the next round reads them through TMA (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        named_bar_sync(1, 128);
+        if (r == 0) {
+          const CUtensorMap* dm = pr.dmap;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
-        tma_store_2d(dm + 1, stg + (h * 2 + 1) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+          for (int h = 0; h < 2; ++h) {
+            tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+            tma_store_2d(dm + 1, stg + (h * 2 + 1) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+          }
+          tma_store_commit();
+        }
+        if (pr.red_out != nullptr) {
+          ssq = warp_sum(ssq);
+          tr = warp_sum(tr);
+          if (lane == 0) { s_red[wq * 2] = ssq; s_red[wq * 2 + 1] = tr; }
+          named_bar_sync(1, 128);
+          if (r == 0) {
+            const int ntj = n / TN;
+            pr.red_out[(ti * ntj + tj) * 2] = (s_red[0] + s_red[2]) + (s_red[4] + s_red[6]);
+            pr.red_out[(ti * ntj + tj) * 2 + 1] = (s_red[1] + s_red[3]) + (s_red[5] + s_red[7]);
+          }
+        }
+        if (r == 0) tma_store_wait_all0();   // stores complete (not only read): the staging smem is free, the data is out
       }
-      tma_store_commit();
+      // ---- end of tile: TMEM drained, staging smem free, every role done
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      tile_parity ^= 1;
     }
-    if (pr.red_out != nullptr) {
-      ssq = warp_sum(ssq);
-      tr = warp_sum(tr);
-      if (lane == 0) { s_red[wq * 2] = ssq; s_red[wq * 2 + 1] = tr; }
-      named_bar_sync(1, 128);
-      if (r == 0) {
-        const int ntj = n / TN;
-        pr.red_out[(ti * ntj + tj) * 2] = (s_red[0] + s_red[2]) + (s_red[4] + s_red[6]);
-        pr.red_out[(ti * ntj + tj) * 2 + 1] = (s_red[1] + s_red[3]) + (s_red[5] + s_red[7]);
+    // ---- grid-wide barrier between two rounds (the last round of the launch ends with the kernel)
+    if (round + 1 < r1) {
+      prefetch_round(round + 1);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ++barriers_done;
+        const unsigned target = barriers_done * gridDim.x;
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        atomicAdd(grid_counter, 1u);
+        if (ld_acquire_gpu_u32(grid_counter) < target) {
+          const long long t0 = clock64();
+          while (ld_acquire_gpu_u32(grid_counter) < target)
+            if (clock64() - t0 > (8ll << 30)) __trap();   // ~4 s at 2 GHz: a lost CTA must not hang the stream
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
       }
+      __syncthreads();
     }
-    if (r == 0) tma_store_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -431,7 +488,7 @@ __global__ void sum_planes_kernel(float* __restrict__ dst, const float* __restri
 int preload_w2_kernels() {
   cudaFuncAttributes fa;
 #define STB_PRELOAD(k) STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)))
-  STB_PRELOAD(w2_gemm_kernel); STB_PRELOAD(w2_cov_kernel); STB_PRELOAD(w2_ns_init_kernel);
+  STB_PRELOAD(w2_chain_kernel); STB_PRELOAD(w2_cov_kernel); STB_PRELOAD(w2_ns_init_kernel);
   STB_PRELOAD(w2_target_finish_kernel); STB_PRELOAD(w2_fwd_finish_kernel); STB_PRELOAD(w2_bwd_finish_kernel);
   STB_PRELOAD(w2_gmu_kernel); STB_PRELOAD(sum_planes_kernel);
 #undef STB_PRELOAD
@@ -530,6 +587,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   }
   d_layers = (W2Layer*)take(sizeof(W2Layer) * 5);
   d_maps = (CUtensorMap*)take(sizeof(CUtensorMap) * MAX_MAPS);
+  d_grid_counter = (unsigned*)take(256);
 
   // ---- build the round lists once (pointers are stable)
   Builder b;
@@ -598,7 +656,9 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   STB_CHECK(b.rc == 0, STB_ERR_CUDA, "W2 round construction failed (%d): %s", b.rc, last_error_string().c_str());
   STB_CHECK((int)b.maps.size() <= MAX_MAPS, STB_ERR_WORKSPACE, "W2 tensor map table overflow (%zu)", b.maps.size());
 
+  d_rounds = (W2Round*)take(sizeof(W2Round) * rounds.size());
   STB_CHECK(off <= bytes, STB_ERR_WORKSPACE, "W2 workspace overflow (%zu > %zu)", off, bytes);
+  STB_CUDA_CHECK(cudaMemcpy(d_rounds, rounds.data(), sizeof(W2Round) * rounds.size(), cudaMemcpyHostToDevice));
   STB_CUDA_CHECK(cudaMemcpy(d_maps, b.maps.data(), sizeof(CUtensorMap) * b.maps.size(), cudaMemcpyHostToDevice));
   STB_CUDA_CHECK(cudaMemcpy(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice));
   return STB_OK;
@@ -607,26 +667,41 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
 int W2Engine::upload_layers(cudaStream_t s) {
   // layer weights enter the Gc round through gamma = w / C (rounds travel as kernel parameters)
   for (int l = 0; l < 5; ++l) rounds[gc_round].probs[4 - l].gamma = host_layers[l].weight / host_layers[l].n;
+  STB_CUDA_CHECK(cudaMemcpyAsync(d_rounds + gc_round, &rounds[gc_round], sizeof(W2Round), cudaMemcpyHostToDevice, s));
   STB_CUDA_CHECK(cudaMemcpyAsync(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice, s));
   return STB_OK;
 }
 
 int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
-  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(w2_gemm_kernel), T_SMEM_BYTES));
-  static const bool pdl = [] { const char* e = getenv("STB_PDL"); return !(e && e[0] == '0'); }();
-  for (int r = r0; r < r1; ++r) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(rounds[r].n_tiles);
-    cfg.blockDim = dim3(T_THREADS);
-    cfg.dynamicSmemBytes = T_SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, w2_gemm_kernel, rounds[r]));
+  if (r1 <= r0) return STB_OK;
+  STB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(w2_chain_kernel), T_SMEM_BYTES));
+  // STB_W2_CHAIN=0: one launch per round (no grid barrier, no cooperative launch) -- diagnostic / fallback
+  static const bool chain = [] { const char* e = getenv("STB_W2_CHAIN"); return !(e && e[0] == '0'); }();
+  const int sms = num_sms();
+  if (!chain) {
+    for (int r = r0; r < r1; ++r) {
+      const int grid = rounds[r].n_tiles < sms ? rounds[r].n_tiles : sms;
+      w2_chain_kernel<<<grid, T_THREADS, T_SMEM_BYTES, s>>>(d_rounds, r, r + 1, d_grid_counter);
+    }
+    STB_CUDA_CHECK(cudaGetLastError());
+    return STB_OK;
   }
+  int max_tiles = 1;
+  for (int r = r0; r < r1; ++r) max_tiles = rounds[r].n_tiles > max_tiles ? rounds[r].n_tiles : max_tiles;
+  STB_CUDA_CHECK(cudaMemsetAsync(d_grid_counter, 0, sizeof(unsigned), s));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(max_tiles < sms ? max_tiles : sms);   // one CTA per SM: all co-resident (cooperative launch)
+  cfg.blockDim = dim3(T_THREADS);
+  cfg.dynamicSmemBytes = T_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const W2Round* dr = d_rounds;
+  unsigned* ctr = d_grid_counter;
+  STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, w2_chain_kernel, dr, r0, r1, ctr));
   return STB_OK;
 }
 
