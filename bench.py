@@ -210,6 +210,11 @@ def run_native(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # exactly ONE line on stdout: libraries (NCCL's version banner, torchrun) print there too, so fd 1 is pointed at
+    # stderr for the duration of the run and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     size = args.size
@@ -433,7 +438,8 @@ def run_native(args, rank, local_rank, world):
                     roofline=roofline, cpu_baseline=cb)
         if parity is not None:
             line['parity_vs_n1'] = parity
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 

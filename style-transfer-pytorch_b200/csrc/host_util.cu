@@ -77,6 +77,23 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
   return STB_OK;
 }
 
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  STB_CHECK(fn != nullptr, STB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  STB_CHECK((reinterpret_cast<uintptr_t>(base) & 127) == 0, STB_ERR_INVALID, "TMA base %p not 128B aligned", base);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  STB_CHECK(r == CUDA_SUCCESS, STB_ERR_CUDA, "cuTensorMapEncodeTiled(f16 2d) failed (%d): %llux%llu box %ux%u", (int)r,
+            (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+  return STB_OK;
+}
+
 int ensure_dynamic_smem(const void* func, int bytes) {
   static std::mutex mu;
   static std::vector<std::pair<const void*, int>> done;  // (kernel, device)

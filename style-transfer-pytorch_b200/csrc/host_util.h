@@ -44,6 +44,10 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
                      uint32_t box_rows);
 
+// 2-D fp16 row-major [rows][cols] tensor map, SWIZZLE_128B (box_cols * 2 bytes must be 128), zero OOB fill.
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                     uint32_t box_rows);
+
 int num_sms();
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember it per (kernel, device) so that contexts

@@ -92,6 +92,8 @@ struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major; a matrix
   int n;
   float alpha, gamma;
   int write_t;  // also write the planes of D^T (D is later used as a right factor)
+  int in_half;  // operands are fp16 plane pairs (hi, lo * 2^11) instead of TF32 pairs: kind::f16 MMAs, half the bytes
+  int out_half; // D is written as an fp16 plane pair
 };
 constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152;
 struct W2Round {  // one grouped GEMM step of all layers; lives in device memory, walked by w2_chain_kernel
@@ -99,7 +101,7 @@ struct W2Round {  // one grouped GEMM step of all layers; lives in device memory
   TcProb probs[W2_MAX_PROBS];
   uint32_t tiles[W2_MAX_TILES];  // prob << 16 | tile row << 8 | tile col
 };
-enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4 };
+enum { W2S_NORM_A = 0, W2S_TR_COV = 1, W2S_TR_COV_T = 2, W2S_MEAN_DIFF = 3, W2S_LOSS = 4, W2S_QSCALE = 5 };
 struct W2Layer {
   int n;            // channels
   float eps;        // 1e-4 (ST:152)
@@ -110,6 +112,8 @@ struct W2Layer {
   float *mean_t, *srm_t, *cov_t, *P;   // target: mean, second raw moment, covariance (pair), sqrtm(cov_t) (pair)
   float *M, *X, *Y[2], *Z[2], *T;      // forward chain (plane pairs)
   float *A[2], *Q[2], *E, *X1, *X23, *U, *Gc, *Gs;  // backward chain (pairs; Gs, X1 single planes)
+  float* Qf;        // the final q of the Lyapunov iteration as a TF32 plane pair (U = P^T q runs on the TF32 path)
+  float* gc_alpha;  // device address of the alpha of this layer's Gc GEMM (w2_fwd_finish patches it: 0.5 / q scale)
   float* gmu_bias;  // out: (d loss / d mean) / npix              -> per-channel bias of the tap-gradient GEMM
   bf16* gs_bf16;    // out: (G + G^T) / npix as bf16 [n][n]       -> B operand of the tap-gradient GEMM
   float* scal;      // W2S_* scalars

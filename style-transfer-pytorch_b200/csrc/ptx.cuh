@@ -158,6 +158,10 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with FP16 A/B (a_format = b_format = 0) and FP32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // kind::tf32 (fp32 containers, 10-bit mantissa used; K = 8 per instruction), both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -27,8 +27,12 @@
 //     style terms by -1e-3 ... -3e-3 at 512^2 and above (the CPU emulation of that schedule in fp32 shows the same),
 //     i.e. above the 1e-3 loss bar.  The full products stay within 3e-4 of the fp64 chain.
 // Tensor maps are encoded once per workspace binding.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <map>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "kernels.h"
@@ -79,6 +83,29 @@ __device__ __forceinline__ void store_split(float* m, size_t nn, size_t e, float
   m[nn + e] = l;
 }
 __device__ __forceinline__ float load2(const float* m, size_t nn, size_t e) { return m[e] + m[nn + e]; }
+
+// fp16 plane pairs (the Newton-Schulz / Lyapunov iterates): x = hi + lo' * 2^-11 with hi = fp16(x) and
+// lo' = fp16((x - hi) * 2^11) -- 22 significant bits like the TF32 pair, in HALF the bytes, and kind::f16 MMAs.  The
+// residual is stored scaled so that it lives in the same exponent range as x (no fp16 underflow); the products
+// lo'_a hi_b + hi_a lo'_b go to their own accumulator, which the epilogue scales by 2^-11.  Every matrix kept this way
+// is normalised (|entries| <~ 1e2), far inside the fp16 range; the un-normalised ones (cov, P, X, M, U, Gc and the
+// final q) stay TF32 pairs.
+constexpr float H_LO_SCALE = 2048.f, H_LO_INV = 1.f / 2048.f;
+__device__ __forceinline__ void split_half(float v, __half& h, __half& l) {
+  h = __float2half_rn(v);
+  l = __float2half_rn((v - __half2float(h)) * H_LO_SCALE);
+}
+__device__ __forceinline__ void store_split_h(float* m, size_t nn, size_t e, float v) {
+  __half* mh = reinterpret_cast<__half*>(m);
+  __half h, l;
+  split_half(v, h, l);
+  mh[e] = h;
+  mh[nn + e] = l;
+}
+__device__ __forceinline__ float load2_h(const float* m, size_t nn, size_t e) {
+  const __half* mh = reinterpret_cast<const __half*>(m);
+  return __half2float(mh[e]) + __half2float(mh[nn + e]) * H_LO_INV;
+}
 
 // D = alpha * A * B + gamma * I on one 128 x 64 tile.  A matrix is 4 planes of n*n floats: hi, lo, hi^T, lo^T.
 // smem per stage: A planes [128 rows][32 k] and B^T planes [64 rows (n)][32 k], all K-major SW128.
@@ -152,8 +179,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
       const TcProb pr = first ? pre_pr : rp.probs[t >> 16];
       const int ti = (t >> 8) & 0xFF, tj = t & 0xFF;
       const int n = pr.n;
-      const int n_k = n / TKF;
-      const int steps_per_acc = (n / 8 + T_MAX_ACC - 1) / T_MAX_ACC;
+      const int k_elems = pr.in_half ? 2 * TKF : TKF;          // elements per 128-byte stage row
+      const int n_k = n / k_elems;
+      const int k_steps = n / (pr.in_half ? 16 : 8);           // MMA K steps of the whole tile
+      const int steps_per_acc = (k_steps + T_MAX_ACC - 1) / T_MAX_ACC;
 
       if (warp == 0) {
         // ---- TMA producer: four planes per stage
@@ -163,10 +192,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], T_STAGE_BYTES);
             uint8_t* st = smem + s * T_STAGE_BYTES;
-            tma_load_2d(st, pr.amap, &full[s], k * TKF, ti * TM);
-            tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * TKF, ti * TM);
-            tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * TKF, tj * TN);  // rows of B^T
-            tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * TKF, tj * TN);
+            tma_load_2d(st, pr.amap, &full[s], k * k_elems, ti * TM);
+            tma_load_2d(st + A_PLANE_BYTES, pr.amap + 1, &full[s], k * k_elems, ti * TM);
+            tma_load_2d(st + 2 * A_PLANE_BYTES, pr.bmap, &full[s], k * k_elems, tj * TN);  // rows of B^T
+            tma_load_2d(st + 2 * A_PLANE_BYTES + B_PLANE_BYTES, pr.bmap + 1, &full[s], k * k_elems, tj * TN);
           }
           if (++s == T_STAGES) { s = 0; ph ^= 1; }
         }
@@ -179,8 +208,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         // runs to seven TMEM accumulators (2 steps each at C = 64 ... 10 at C = 512), the small cross terms go to an
         // eighth, and the epilogue adds all of them in round-to-nearest fp32.
         constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+        constexpr uint32_t idesc_h = umma_idesc_f16(TM, TN);
         constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
         const bool leader = elect_one();
+        const bool half_in = pr.in_half != 0;
         for (int k = 0; k < n_k; ++k) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -189,13 +220,24 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
             const uint32_t a_h = umma_desc_lo(base), a_l = umma_desc_lo(base + A_PLANE_BYTES);
             const uint32_t b_h = umma_desc_lo(base + 2 * A_PLANE_BYTES);
             const uint32_t b_l = umma_desc_lo(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+            if (!half_in) {
 #pragma unroll
-            for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
-              const int step = k * (TKF / 8) + kk;
-              const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
-              umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
-              umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
-              umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
+              for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
+                const int step = k * (TKF / 8) + kk;
+                const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+                umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
+                umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
+                umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
+              }
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {        // 16 halfs = 32 bytes per K step -> +2 in the descriptor
+                const int step = k * 4 + kk;
+                const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+                umma_bf16_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc_h, step > 0);
+                umma_bf16_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc_h, 1);
+                umma_bf16_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc_h, step % steps_per_acc > 0);
+              }
             }
             umma_commit(&empty[s]);
           }
@@ -214,8 +256,11 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         mbar_wait(t_full, tile_parity);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-        const int n_chunks = (n / 8 + steps_per_acc - 1) / steps_per_acc;
+        const int n_chunks = (k_steps + steps_per_acc - 1) / steps_per_acc;
         const bool valid = gi < n;
+        const float cross_scale = pr.in_half ? H_LO_INV : 1.f;   // fp16 pairs keep the residual plane times 2^11
+        const bool half_out = pr.out_half != 0;
+        __half* Dh = reinterpret_cast<__half*>(pr.D);
         float ssq = 0.f, tr = 0.f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -234,27 +279,53 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
           tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
           tmem_ld_wait();
           const int gj0 = tj * TN + h * 32;
-          uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
-          uint8_t* row_lo = row_hi + A_PLANE_BYTES;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float vh[4], vl[4];
+          for (int e = 0; e < 32; ++e) {   // finished values of this row's 32 columns
+            float o = (acc[e] + __uint_as_float(v[e]) * cross_scale) * pr.alpha;
+            if (gi == gj0 + e) { o += pr.gamma; tr += o; }
+            if (valid) ssq = fmaf(o, o, ssq);
+            acc[e] = o;
+          }
+          if (!half_out) {
+            uint8_t* row_hi = stg + (h * 2) * A_PLANE_BYTES + r * 128;
+            uint8_t* row_lo = row_hi + A_PLANE_BYTES;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float o = (acc[4 * q + e] + __uint_as_float(v[4 * q + e])) * pr.alpha;
-              if (gi == gj0 + 4 * q + e) { o += pr.gamma; tr += o; }
-              if (valid) ssq = fmaf(o, o, ssq);
-              split_tf32(o, vh[e], vl[e]);
+            for (int q = 0; q < 8; ++q) {
+              float vh[4], vl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32(acc[4 * q + e], vh[e], vl[e]);
+              const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
+              *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+              *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+              if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 B
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const size_t at = 2 * nn + (size_t)(gj0 + 4 * q + e) * n + gi;
+                  pr.D[at] = vh[e];
+                  pr.D[nn + at] = vl[e];
+                }
+              }
             }
-            const int chunk = (q ^ (r & 7)) * 16;  // 128-byte swizzle, as the TMA store expects
-            *reinterpret_cast<float4*>(row_hi + chunk) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-            *reinterpret_cast<float4*>(row_lo + chunk) = make_float4(vl[0], vl[1], vl[2], vl[3]);
-            if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes (consecutive rows) write 128 B
+          } else {
+            // fp16 pair: one 128 x 64 tile per plane (row = 64 halfs = 128 bytes), hi plane at stg, lo plane after it;
+            // this half of the row fills 16-byte chunks 4h .. 4h+3
+            uint8_t* row_hi = stg + r * 128;
+            uint8_t* row_lo = row_hi + A_PLANE_BYTES;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const size_t at = 2 * nn + (size_t)(gj0 + 4 * q + e) * n + gi;
-                pr.D[at] = vh[e];
-                pr.D[nn + at] = vl[e];
+            for (int q = 0; q < 4; ++q) {
+              __half hh[8], ll[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split_half(acc[8 * q + e], hh[e], ll[e]);
+              const int chunk = ((h * 4 + q) ^ (r & 7)) * 16;
+              *reinterpret_cast<uint4*>(row_hi + chunk) = *reinterpret_cast<const uint4*>(hh);
+              *reinterpret_cast<uint4*>(row_lo + chunk) = *reinterpret_cast<const uint4*>(ll);
+              if (pr.write_t && valid) {  // D^T planes: for a fixed column the 32 lanes write 64 contiguous bytes
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const size_t at = 2 * nn + (size_t)(gj0 + 8 * q + e) * n + gi;
+                  Dh[at] = hh[e];
+                  Dh[nn + at] = ll[e];
+                }
               }
             }
           }
@@ -266,10 +337,15 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         named_bar_sync(1, 128);
         if (r == 0) {
           const CUtensorMap* dm = pr.dmap;
+          if (!half_out) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
-            tma_store_2d(dm + 1, stg + (h * 2 + 1) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+            for (int h = 0; h < 2; ++h) {
+              tma_store_2d(dm, stg + (h * 2) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+              tma_store_2d(dm + 1, stg + (h * 2 + 1) * A_PLANE_BYTES, tj * TN + h * 32, ti * TM);
+            }
+          } else {
+            tma_store_2d(dm, stg, tj * TN, ti * TM);
+            tma_store_2d(dm + 1, stg + A_PLANE_BYTES, tj * TN, ti * TM);
           }
           tma_store_commit();
         }
@@ -401,10 +477,12 @@ __global__ void __launch_bounds__(256) w2_ns_init_kernel(const W2Layer* __restri
   const float norm = sqrtf(ss);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    store_split(L.Y[0], nn, e, load2(M, nn, e) / norm);
-    store_split(L.Y[0] + 2 * nn, nn, e, load2(M + 2 * nn, nn, e) / norm);  // Y^T from the planes of M^T (cov_t: symmetric)
-    const float z0 = (i == j) ? 1.f : 0.f;
-    L.Z[0][e] = z0; L.Z[0][nn + e] = 0.f; L.Z[0][2 * nn + e] = z0; L.Z[0][3 * nn + e] = 0.f;
+    // Y, Z are fp16 plane pairs: planes hi, lo', hi^T, lo'^T of n*n HALFS each
+    store_split_h(L.Y[0], nn, e, load2(M, nn, e) / norm);
+    store_split_h(L.Y[0], nn, 2 * nn + e, load2(M + 2 * nn, nn, e) / norm);  // Y^T from the planes of M^T (cov_t: symmetric)
+    const __half z0 = __float2half_rn((i == j) ? 1.f : 0.f), zero = __float2half_rn(0.f);
+    __half* Zh = reinterpret_cast<__half*>(L.Z[0]);
+    Zh[e] = z0; Zh[nn + e] = zero; Zh[2 * nn + e] = z0; Zh[3 * nn + e] = zero;
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) L.scal[W2S_NORM_A] = norm;
 }
@@ -416,8 +494,8 @@ __global__ void __launch_bounds__(256) w2_target_finish_kernel(const W2Layer* __
   const size_t nn = (size_t)n * n;
   const float s = sqrtf(L.scal[W2S_NORM_A]);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
-    store_split(L.P, nn, e, load2(L.Y[0], nn, e) * s);
-    store_split(L.P + 2 * nn, nn, e, load2(L.Y[0] + 2 * nn, nn, e) * s);  // P^T from the planes of Y^T
+    store_split(L.P, nn, e, load2_h(L.Y[0], nn, e) * s);
+    store_split(L.P + 2 * nn, nn, e, load2_h(L.Y[0], nn, 2 * nn + e) * s);  // P^T from the planes of Y^T
   }
 }
 
@@ -435,15 +513,21 @@ __global__ void __launch_bounds__(256) w2_fwd_finish_kernel(const W2Layer* __res
   const float norm_r = sq * norm_y;                     // ||R||_F
   const float tr_r = tr * sq;
   const float seed = -2.f * L.weight / (n * norm_r);    // grad_output / ||z|| with grad_output = -2 w / C * I
+  // q only ever enters linearly (q' = q E / 2, U = P^T q, Gc = U P^T / 2): the iteration runs on q * 2^k with
+  // |seed| * 2^k in [0.5, 1), which keeps the fp16 pair of a 1e-5-sized seed out of the subnormals; 2^-k goes into the
+  // alpha of the Gc GEMM (exact powers of two: no rounding changes)
+  const float qscale = (fabsf(seed) > 0.f && isfinite(seed)) ? exp2f(-floorf(log2f(fabsf(seed))) - 1.f) : 1.f;
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n * n; e += NB * 256) {
     const int i = e / n, j = e - i * n;
-    store_split(L.A[0], nn, e, load2(L.Y[0], nn, e) / norm_y);   // a = z / ||z||
-    store_split(L.A[0] + 2 * nn, nn, e, load2(L.Y[0] + 2 * nn, nn, e) / norm_y);
-    const float q0 = (i == j) ? seed : 0.f;
-    store_split(L.Q[0], nn, e, q0);
-    store_split(L.Q[0] + 2 * nn, nn, e, q0);
+    store_split_h(L.A[0], nn, e, load2_h(L.Y[0], nn, e) / norm_y);   // a = z / ||z||
+    store_split_h(L.A[0], nn, 2 * nn + e, load2_h(L.Y[0], nn, 2 * nn + e) / norm_y);
+    const float q0 = (i == j) ? seed * qscale : 0.f;
+    store_split_h(L.Q[0], nn, e, q0);
+    store_split_h(L.Q[0], nn, 2 * nn + e, q0);
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) {
+    L.scal[W2S_QSCALE] = qscale;
+    *L.gc_alpha = 0.5f / qscale;
     const float cov_diff = (L.scal[W2S_TR_COV_T] + L.scal[W2S_TR_COV] - 2.f * tr_r) / n;
     const float l = (L.scal[W2S_MEAN_DIFF] + cov_diff) * L.weight;
     L.scal[W2S_LOSS] = l;
@@ -503,8 +587,9 @@ int W2Engine::read_matrix(float* dst, const float* pair, int n, cudaStream_t s) 
 
 // ================================================================================================ host engine
 size_t W2Engine::layer_floats(int n) {
-  // 4 planes (hi, lo, hi^T, lo^T): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t (17); single: Gs, srm_t, X1
-  return (size_t)(17 * 4 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
+  // 4 planes (hi, lo, hi^T, lo^T): cov, M, X, Y[2], Z[2], T, A[2], Q[2], E, U, Gc, P, cov_t, Qf (18); single: Gs, srm_t, X1
+  // (the fp16 pairs Y, Z, T, A, Q, E use half of their slot)
+  return (size_t)(18 * 4 + 3) * n * n + 8 * (size_t)n + 64 + 2 * NRED + 1024;
 }
 
 size_t W2Engine::workspace_bytes() {
@@ -520,18 +605,29 @@ struct Builder {
   std::vector<W2Round>* rounds = nullptr;
   std::vector<CUtensorMap> maps;
   std::map<const float*, int> map_index;
+  std::set<const float*> half_mats;   // matrices kept as fp16 plane pairs (4 planes of n*n halfs at the slot's start)
   CUtensorMap* d_maps = nullptr;
   int rc = 0;
+  bool is_half(const float* m) const { return half_mats.count(m) != 0; }
   int maps_for(const float* m, int n) {
     auto it = map_index.find(m);
     if (it != map_index.end()) return it->second;
     const int idx = (int)maps.size();
     maps.resize(idx + 4);
     const size_t nn = (size_t)n * n;
-    int r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);               // 128-row boxes: A loads, D stores
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m + 2 * nn, n, n, TKF, TN);  // 64-row boxes on the planes of the
-    if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + 3 * nn, n, n, TKF, TN);  // transpose: B loads
+    int r;
+    if (is_half(m)) {
+      const __half* h = reinterpret_cast<const __half*>(m);
+      r = make_tmap_f16_2d(&maps[idx + 0], h, n, n, 2 * TKF, TM);               // 64 halfs = 128 bytes per box row
+      if (!r) r = make_tmap_f16_2d(&maps[idx + 1], h + nn, n, n, 2 * TKF, TM);
+      if (!r) r = make_tmap_f16_2d(&maps[idx + 2], h + 2 * nn, n, n, 2 * TKF, TN);
+      if (!r) r = make_tmap_f16_2d(&maps[idx + 3], h + 3 * nn, n, n, 2 * TKF, TN);
+    } else {
+      r = make_tmap_f32_2d(&maps[idx + 0], m, n, n, TKF, TM);               // 128-row boxes: A loads, D stores
+      if (!r) r = make_tmap_f32_2d(&maps[idx + 1], m + nn, n, n, TKF, TM);
+      if (!r) r = make_tmap_f32_2d(&maps[idx + 2], m + 2 * nn, n, n, TKF, TN);  // 64-row boxes on the planes of the
+      if (!r) r = make_tmap_f32_2d(&maps[idx + 3], m + 3 * nn, n, n, TKF, TN);  // transpose: B loads
+    }
     if (r) rc = r;
     map_index[m] = idx;
     return idx;
@@ -550,6 +646,9 @@ struct Builder {
     p.bmap = d_maps + maps_for(b_t ? B - 2 * nn : B, n) + 2;
     p.dmap = d_maps + maps_for(D, n);
     p.D = D; p.red_out = red_out; p.n = n; p.alpha = alpha; p.gamma = gamma; p.write_t = write_t;
+    p.in_half = is_half(A) ? 1 : 0;
+    p.out_half = is_half(D) ? 1 : 0;
+    if (is_half(A) != is_half(B) || ((a_t || b_t) && is_half(A))) { rc = STB_ERR_STATE; return; }
     for (int i = 0; i < (n + TM - 1) / TM; ++i)
       for (int j = 0; j < n / TN; ++j) {
         if (R.n_tiles >= W2_MAX_TILES) { rc = STB_ERR_STATE; return; }
@@ -558,7 +657,7 @@ struct Builder {
     ++R.n_probs;
   }
 };
-constexpr int MAX_MAPS = 5 * 28 * 4;
+constexpr int MAX_MAPS = 5 * 32 * 4;
 }  // namespace
 
 int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
@@ -577,6 +676,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     L.T = (float*)take(pp); L.A[0] = (float*)take(pp); L.A[1] = (float*)take(pp);
     L.Q[0] = (float*)take(pp); L.Q[1] = (float*)take(pp); L.E = (float*)take(pp);
     L.U = (float*)take(pp); L.Gc = (float*)take(pp); L.P = (float*)take(pp); L.cov_t = (float*)take(pp);
+    L.Qf = (float*)take(pp);
     L.Gs = (float*)take(nn); L.srm_t = (float*)take(nn); L.X1 = (float*)take(nn); L.X23 = nullptr;
     L.S_raw = nullptr; L.sums = nullptr;  // bound per plan (stats buffer)
     L.mu = (float*)take(n * 4); L.mean_t = (float*)take(n * 4); L.gmu_bias = (float*)take(n * 4);
@@ -594,6 +694,10 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   b.d_maps = d_maps;
   b.rounds = &rounds;
   rounds.clear();
+  for (int l = 0; l < 5; ++l) {  // the normalised iterates of both iterations live as fp16 plane pairs
+    W2Layer& L = host_layers[l];
+    for (float* m : {L.Y[0], L.Y[1], L.Z[0], L.Z[1], L.T, L.A[0], L.A[1], L.Q[0], L.Q[1], L.E}) b.half_mats.insert(m);
+  }
   auto begin_round = [&]() { b.begin_round(); };
   auto end_round = [&]() {};
   auto ns_rounds = [&]() {  // 12 x { T = 1.5 I - 0.5 Z Y ; Y' = Y T, Z' = T Z }, result ends in Y[0]
@@ -639,14 +743,15 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
     begin_round();
     for (int l = 4; l >= 0; --l) {
       W2Layer& L = host_layers[l];
-      b.add(L.n, L.Q[d], L.Q[s], L.E, 0.5f);
+      b.add(L.n, it == 11 ? L.Qf : L.Q[d], L.Q[s], L.E, 0.5f);   // the final q leaves the iteration as a TF32 pair
       if (it < 11) b.add(L.n, L.A[d], L.A[s], L.E, 0.5f);
     }
     end_round();
   }
-  // after 12 its q is in Q[0].  U = P^T q ; Gc = 0.5 U P^T + (w/C) I   (gamma patched per layer in upload_layers)
+  // after 12 its q (times the layer's power-of-two q scale) is in Qf.  U = P^T q ; Gc = alpha U P^T + (w/C) I with
+  // alpha = 0.5 / qscale patched on the device by w2_fwd_finish_kernel, gamma per layer in upload_layers
   begin_round();
-  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Q[0], 1.f, 0.f, nullptr, 0, 1, 0); }
+  for (int l = 4; l >= 0; --l) { W2Layer& L = host_layers[l]; b.add(L.n, L.U, L.P, L.Qf, 1.f, 0.f, nullptr, 0, 1, 0); }
   end_round();
   begin_round();
   gc_round = (int)rounds.size() - 1;
@@ -659,6 +764,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   d_rounds = (W2Round*)take(sizeof(W2Round) * rounds.size());
   STB_CHECK(off <= bytes, STB_ERR_WORKSPACE, "W2 workspace overflow (%zu > %zu)", off, bytes);
   STB_CUDA_CHECK(cudaMemcpy(d_rounds, rounds.data(), sizeof(W2Round) * rounds.size(), cudaMemcpyHostToDevice));
+  for (int l = 0; l < 5; ++l) host_layers[l].gc_alpha = &d_rounds[gc_round].probs[4 - l].alpha;
   STB_CUDA_CHECK(cudaMemcpy(d_maps, b.maps.data(), sizeof(CUtensorMap) * b.maps.size(), cudaMemcpyHostToDevice));
   STB_CUDA_CHECK(cudaMemcpy(d_layers, host_layers, sizeof(W2Layer) * 5, cudaMemcpyHostToDevice));
   return STB_OK;
