@@ -54,7 +54,8 @@ constexpr int T_OFF_BAR = T_STAGES * T_STAGE_BYTES;
 constexpr int T_OFF_TMEMPTR = T_OFF_BAR + (2 * T_STAGES + 1) * 8;
 constexpr int T_OFF_RED = T_OFF_TMEMPTR + 16;
 constexpr int T_SMEM_BYTES = T_OFF_RED + 64 + 1024;
-constexpr int T_THREADS = 64 + 128;
+constexpr int T_EPI_THREADS = 256;                 // two epilogue groups of four warps: one per 32-column half of the tile
+constexpr int T_THREADS = 64 + T_EPI_THREADS;
 constexpr int NRED = 128;  // max reduction partials per layer
 constexpr int NB = 128;    // helper-kernel CTAs per layer: they are latency-bound element-wise passes (32 CTAs: 48 us)
 static_assert(NB <= NRED, "the covariance kernel writes one partial per CTA");
@@ -247,8 +248,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         if (leader) umma_commit(t_full);
         __syncwarp();
       } else {
-        // ---- epilogue (128 threads, TMEM lane = tile row)
+        // ---- epilogue (2 groups x 128 threads, TMEM lane = tile row; group g drains columns [32 g, 32 g + 32))
         const int wq = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const bool issuer = warp == 2 && lane == 0;   // the one thread that issues the TMA stores / writes the partials
         const int r = wq * 32 + lane;
         const int gi = ti * TM + r;
         const size_t nn = (size_t)n * n;
@@ -262,19 +265,30 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         const bool half_out = pr.out_half != 0;
         __half* Dh = reinterpret_cast<__half*>(pr.D);
         float ssq = 0.f, tr = 0.f;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
+        {
+          const int h = grp;
+          uint32_t v[32], v2[32];
           float acc[32];
+          // chunk sums in the same order as ever (c = 0, 1, 2, ...); the TMEM loads go out in pairs under one wait
           tmem_ld_32x32(taddr + h * 32, v);
+          if (n_chunks > 1) tmem_ld_32x32(taddr + TN + h * 32, v2);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
-          for (int c = 1; c < n_chunks; ++c) {
+          if (n_chunks > 1) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v2[e]);
+          }
+          for (int c = 2; c < n_chunks; c += 2) {
             tmem_ld_32x32(taddr + c * TN + h * 32, v);
+            if (c + 1 < n_chunks) tmem_ld_32x32(taddr + (c + 1) * TN + h * 32, v2);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v[e]);
+            if (c + 1 < n_chunks) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v2[e]);
+            }
           }
           tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
           tmem_ld_wait();
@@ -334,8 +348,8 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         fence_proxy_async_smem();
         // the D^T planes were written through the generic proxy; the next round reads them through TMA (async proxy)
         asm volatile("fence.proxy.async;" ::: "memory");
-        named_bar_sync(1, 128);
-        if (r == 0) {
+        named_bar_sync(1, T_EPI_THREADS);
+        if (issuer) {
           const CUtensorMap* dm = pr.dmap;
           if (!half_out) {
 #pragma unroll
@@ -352,15 +366,17 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         if (pr.red_out != nullptr) {
           ssq = warp_sum(ssq);
           tr = warp_sum(tr);
-          if (lane == 0) { s_red[wq * 2] = ssq; s_red[wq * 2 + 1] = tr; }
-          named_bar_sync(1, 128);
-          if (r == 0) {
+          if (lane == 0) { s_red[(grp * 4 + wq) * 2] = ssq; s_red[(grp * 4 + wq) * 2 + 1] = tr; }
+          named_bar_sync(1, T_EPI_THREADS);
+          if (issuer) {
             const int ntj = n / TN;
-            pr.red_out[(ti * ntj + tj) * 2] = (s_red[0] + s_red[2]) + (s_red[4] + s_red[6]);
-            pr.red_out[(ti * ntj + tj) * 2 + 1] = (s_red[1] + s_red[3]) + (s_red[5] + s_red[7]);
+            pr.red_out[(ti * ntj + tj) * 2] = ((s_red[0] + s_red[2]) + (s_red[4] + s_red[6])) +
+                                              ((s_red[8] + s_red[10]) + (s_red[12] + s_red[14]));
+            pr.red_out[(ti * ntj + tj) * 2 + 1] = ((s_red[1] + s_red[3]) + (s_red[5] + s_red[7])) +
+                                                  ((s_red[9] + s_red[11]) + (s_red[13] + s_red[15]));
           }
         }
-        if (r == 0) tma_store_wait_all0();   // stores complete (not only read): the staging smem is free, the data is out
+        if (issuer) tma_store_wait_all0();   // stores complete (not only read): the staging smem is free, the data is out
       }
       // ---- end of tile: TMEM drained, staging smem free, every role done
       tc_fence_before();
