@@ -157,6 +157,10 @@ STB_API int stb_profile_enable(stb_ctx* ctx, int enable);
 STB_API int stb_profile_read(stb_ctx* ctx, float* ms_out, int* count_out, int n_classes);
 
 /* ------------------------------------------------------------------ diagnostics
+ * stb_debug_w2_trace (with STB_W2_TRACE=1 in the environment): per-round %globaltimer stamps of CTA 0 of the W2 chain
+ * kernel, 8 words per round for up to 128 rounds (tools/w2_trace.py prints the timeline). */
+STB_API int stb_debug_w2_trace(stb_ctx* ctx, unsigned long long* host_out, size_t words, int* rounds_out);
+/*
  * Copy of an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward. */
 STB_API int stb_debug_activation(stb_ctx* ctx, int H, int W, int conv_index, void* out_bf16, size_t out_bytes,
                                  void* stream);

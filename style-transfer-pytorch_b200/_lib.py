@@ -61,6 +61,7 @@ def _declare(lib):
         'stb_profile_enable': [vp, i],
         'stb_profile_read': [vp, C.POINTER(f), C.POINTER(i), i],
         'stb_debug_activation': [vp, i, i, i, vp, sz, vp],
+        'stb_debug_w2_trace': [vp, vp, sz, C.POINTER(i)],
     })
     lib.stb_ctx_destroy.argtypes = [vp]
     lib.stb_ctx_destroy.restype = None
@@ -93,7 +94,7 @@ EXPORTS = [
     'stb_set_band', 'stb_stats_block', 'stb_iterate_fwd', 'stb_iterate_bwd', 'stb_adam_update',
     'stb_set_loss_ring', 'stb_resize', 'stb_comm_create', 'stb_comm_connect_ipc', 'stb_comm_connect_local', 'stb_comm_disconnect',
     'stb_comm_set_geometry', 'stb_comm_reset',
-    'stb_iterate_banded', 'stb_graph_status', 'stb_launch_count', 'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation',
+    'stb_iterate_banded', 'stb_graph_status', 'stb_launch_count', 'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation', 'stb_debug_w2_trace',
 ]
 # include/stb200_test.h (libstb200_test.so)
 TEST_EXPORTS = [

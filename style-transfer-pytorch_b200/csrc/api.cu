@@ -1078,6 +1078,17 @@ int stb_launch_count(stb_ctx* ctx, int64_t* graph_replays, int64_t* kernels_repl
   return STB_OK;
 }
 
+// diagnostics (STB_W2_TRACE=1): the %globaltimer stamps CTA 0 of the W2 chain kernel wrote for the rounds of the last
+// iteration (8 words per round, see w2_chain_kernel); rounds_out receives the number of rounds.
+int stb_debug_w2_trace(stb_ctx* ctx, unsigned long long* host_out, size_t words, int* rounds_out) {
+  STB_ENTER(ctx);
+  STB_CHECK(ctx->w2_ready && host_out && words >= (size_t)W2_TRACE_WORDS, STB_ERR_INVALID, "need %d words", W2_TRACE_WORDS);
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  STB_CUDA_CHECK(cudaMemcpy(host_out, ctx->w2.d_trace, W2_TRACE_WORDS * 8, cudaMemcpyDeviceToHost));
+  if (rounds_out) *rounds_out = (int)ctx->w2.rounds.size();
+  return STB_OK;
+}
+
 // test hook: copy an internal activation (post-ReLU output of conv `conv_index`, bf16 NHWC) of the last forward
 int stb_debug_activation(stb_ctx* ctx, int H, int W, int conv_index, void* out_bf16, size_t out_bytes, void* stream) {
   STB_CHECK(ctx && out_bf16 && conv_index >= 0 && conv_index < NCONV, STB_ERR_INVALID, "bad argument");

@@ -70,6 +70,7 @@ struct KParams {
   float cscale;
   int row_lo, row_hi;
   int pooling;  // MODE 0: -1 = none, else STB_POOL_*: also emit the 2x2-pooled output (tmPool)
+  int mma_interleave;  // issue order of the MT sub-tiles' MMAs (see the issuer loop)
 };
 
 template <int BN, int MODE>
@@ -187,12 +188,23 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             if (leader) {
               const uint32_t b_lo = umma_desc_lo(b_base0 + sb * C::B_STAGE_BYTES);
-#pragma unroll
-              for (int m = 0; m < C::MT; ++m) {
-                const uint32_t a_lo = umma_desc_lo(a_stage + dy * C::A_PITCH + m * 1024);
+              // k outer, sub-tile inner: two consecutive MMAs never accumulate into the same TMEM tile (a dependent
+              // tcgen05.mma waits for its predecessor's accumulator; STB_MMA_ORDER=0 restores sub-tile-major order)
+              if (p.mma_interleave) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16_split(tmem_d + m * BN, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum | (k > 0));
+#pragma unroll
+                  for (int m = 0; m < C::MT; ++m)
+                    umma_bf16_split(tmem_d + m * BN, umma_desc_lo(a_stage + dy * C::A_PITCH + m * 1024) + 2 * k, a_hi,
+                                    b_lo + 2 * k, b_hi, idesc, accum | (k > 0));
+              } else {
+#pragma unroll
+                for (int m = 0; m < C::MT; ++m) {
+                  const uint32_t a_lo = umma_desc_lo(a_stage + dy * C::A_PITCH + m * 1024);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_split(tmem_d + m * BN, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum | (k > 0));
+                }
               }
               umma_commit(&b_empty[sb]);
               if (dy == 2) umma_commit(&a_empty[sa]);
@@ -439,6 +451,8 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   kp.a2_row0 = a.a2_row0;
   kp.bias = a.bias; kp.mask_src = a.mask_src; kp.ctarget = a.ctarget; kp.cscale = a.cscale;
   kp.row_lo = a.row_lo; kp.row_hi = a.row_hi;
+  static const int mma_order = [] { const char* e = getenv("STB_MMA_ORDER"); return (e && e[0] == '0') ? 0 : 1; }();
+  kp.mma_interleave = mma_order;
   STB_CHECK(a.mode >= 0 && a.mode <= 2, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
   if (a.mode == 1) STB_CHECK(a.mask_src != nullptr, STB_ERR_INVALID, "pixel_gemm: bwd needs mask_src");
 

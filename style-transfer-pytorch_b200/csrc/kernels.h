@@ -95,7 +95,7 @@ struct TcProb {  // D = alpha * A * B + gamma * I, all n x n row-major; a matrix
   int in_half;  // operands are fp16 plane pairs (hi, lo * 2^11) instead of TF32 pairs: kind::f16 MMAs, half the bytes
   int out_half; // D is written as an fp16 plane pair
 };
-constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152;
+constexpr int W2_MAX_PROBS = 10, W2_MAX_TILES = 152, W2_TRACE_WORDS = 8 * 128;
 struct W2Round {  // one grouped GEMM step of all layers; lives in device memory, walked by w2_chain_kernel
   int n_tiles, n_probs;
   TcProb probs[W2_MAX_PROBS];
@@ -125,6 +125,7 @@ struct W2Engine {
   CUtensorMap* d_maps = nullptr;
   W2Round* d_rounds = nullptr;        // device copy of `rounds` (the chain kernel walks it)
   unsigned* d_grid_counter = nullptr; // grid barrier of the chain kernel (zeroed before every launch)
+  unsigned long long* d_trace = nullptr;  // STB_W2_TRACE=1: 8 %globaltimer stamps per round written by CTA 0
   std::vector<W2Round> rounds;
   int r_target_begin = 0, r_target_end = 0, r_fwd_begin = 0, r_fwd_ns_begin = 0, r_fwd_end = 0, r_bwd_begin = 0,
       r_bwd_end = 0, gc_round = 0;

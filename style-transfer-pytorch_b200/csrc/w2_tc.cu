@@ -44,9 +44,14 @@ namespace {
 
 constexpr int TM = 128, TN = 64, TKF = 32;      // tile rows / cols, k floats per stage (128 B swizzle row)
 constexpr int T_STAGES = 4;
-constexpr int T_MAX_ACC = 7;                       // hi*hi accumulators: the K8 steps are dealt out to them in runs
-constexpr int T_TMEM_COLS = 512;                   // 7 x 64 hi*hi accumulators + 64 for the cross terms
-constexpr int T_CROSS_COL = T_MAX_ACC * TN;
+// TMEM: T_MAX_ACC hi*hi accumulators + two for the cross terms (lo*hi and hi*lo apart), 64 columns each.  The k-steps
+// are dealt to the hi*hi accumulators ROUND-ROBIN: each still sums n_steps / T_MAX_ACC products (short truncating
+// chains, section 5 of DESIGN.md), but consecutive MMAs never target the same accumulator -- a tcgen05.mma that
+// accumulates into the tile its predecessor is still writing waits for it (measured: ~125 cycles per MMA in dependent
+// order vs the 32 its math takes).
+constexpr int T_MAX_ACC = 6;
+constexpr int T_TMEM_COLS = 512;
+constexpr int T_CROSS_COL = T_MAX_ACC * TN;        // lo*hi at T_CROSS_COL, hi*lo at T_CROSS_COL + TN
 constexpr int A_PLANE_BYTES = TM * 128;          // 16 KiB
 constexpr int B_PLANE_BYTES = TN * 128;          // 8 KiB
 constexpr int T_STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 48 KiB
@@ -124,7 +129,18 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
 // phase: barrier init, TMEM allocation and the launch / drain latency of a grid are paid once, a round boundary costs
 // one atomic + one acquire spin (~1.5 us instead of ~4 us of launch gap).  The arithmetic of a tile is unchanged.
 __global__ void __launch_bounds__(T_THREADS, 1)
-w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __restrict__ grid_counter) {
+w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __restrict__ grid_counter,
+                unsigned long long* __restrict__ trace) {
+  // trace (STB_W2_TRACE=1, diagnostics): CTA 0 stamps %globaltimer at 8 points of every round --
+  // 0 round start, 1 first stage landed, 2 accumulators complete, 3 tile staged + TMA stores issued, 4 stores complete,
+  // 5 arrived at the grid barrier, 6 barrier passed
+  auto stamp = [&](int round, int k) {
+    if (trace != nullptr && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      trace[round * 8 + k] = t;
+    }
+  };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + T_OFF_BAR);
@@ -183,11 +199,11 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
       const int k_elems = pr.in_half ? 2 * TKF : TKF;          // elements per 128-byte stage row
       const int n_k = n / k_elems;
       const int k_steps = n / (pr.in_half ? 16 : 8);           // MMA K steps of the whole tile
-      const int steps_per_acc = (k_steps + T_MAX_ACC - 1) / T_MAX_ACC;
 
       if (warp == 0) {
         // ---- TMA producer: four planes per stage
         const bool leader = elect_one();   // every lane walks the ring state, the elected one issues
+        if (leader && first) stamp(round, 0);
         for (int k = 0; k < n_k; ++k) {
           if (leader) {
             mbar_wait(&empty[s], ph ^ 1);
@@ -216,6 +232,7 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         for (int k = 0; k < n_k; ++k) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (leader && first && k == 0) stamp(round, 1);
           if (leader) {
             const uint32_t base = smem_u32(smem + s * T_STAGE_BYTES);
             const uint32_t a_h = umma_desc_lo(base), a_l = umma_desc_lo(base + A_PLANE_BYTES);
@@ -225,19 +242,19 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
 #pragma unroll
               for (int kk = 0; kk < TKF / 8; ++kk) {  // 8 floats = 32 bytes per K step -> +2 in the descriptor
                 const int step = k * (TKF / 8) + kk;
-                const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+                const uint32_t t_main = tmem_base + (step % T_MAX_ACC) * TN, t_cross = tmem_base + T_CROSS_COL;
                 umma_tf32_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step > 0);
-                umma_tf32_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, 1);
-                umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step % steps_per_acc > 0);
+                umma_tf32_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc, step >= T_MAX_ACC);
+                umma_tf32_split(t_cross + TN, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc, step > 0);
               }
             } else {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {        // 16 halfs = 32 bytes per K step -> +2 in the descriptor
                 const int step = k * 4 + kk;
-                const uint32_t t_main = tmem_base + (step / steps_per_acc) * TN, t_cross = tmem_base + T_CROSS_COL;
+                const uint32_t t_main = tmem_base + (step % T_MAX_ACC) * TN, t_cross = tmem_base + T_CROSS_COL;
                 umma_bf16_split(t_cross, a_l + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc_h, step > 0);
-                umma_bf16_split(t_cross, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc_h, 1);
-                umma_bf16_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc_h, step % steps_per_acc > 0);
+                umma_bf16_split(t_main, a_h + 2 * kk, dhi, b_h + 2 * kk, dhi, idesc_h, step >= T_MAX_ACC);
+                umma_bf16_split(t_cross + TN, a_h + 2 * kk, dhi, b_l + 2 * kk, dhi, idesc_h, step > 0);
               }
             }
             umma_commit(&empty[s]);
@@ -258,8 +275,9 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         uint8_t* stg = smem + STG_OFF;
         mbar_wait(t_full, tile_parity);
         tc_fence_after();
+        if (issuer && first) stamp(round, 2);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-        const int n_chunks = (k_steps + steps_per_acc - 1) / steps_per_acc;
+        const int n_chunks = k_steps < T_MAX_ACC ? k_steps : T_MAX_ACC;   // hi*hi accumulators in use
         const bool valid = gi < n;
         const float cross_scale = pr.in_half ? H_LO_INV : 1.f;   // fp16 pairs keep the residual plane times 2^11
         const bool half_out = pr.out_half != 0;
@@ -291,7 +309,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
             }
           }
           tmem_ld_32x32(taddr + T_CROSS_COL + h * 32, v);
+          tmem_ld_32x32(taddr + T_CROSS_COL + TN + h * 32, v2);
           tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
           const int gj0 = tj * TN + h * 32;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {   // finished values of this row's 32 columns
@@ -362,6 +383,7 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
             tma_store_2d(dm + 1, stg + A_PLANE_BYTES, tj * TN, ti * TM);
           }
           tma_store_commit();
+          if (first) stamp(round, 3);
         }
         if (pr.red_out != nullptr) {
           ssq = warp_sum(ssq);
@@ -376,7 +398,10 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
                                                   ((s_red[9] + s_red[11]) + (s_red[13] + s_red[15]));
           }
         }
-        if (issuer) tma_store_wait_all0();   // stores complete (not only read): the staging smem is free, the data is out
+        if (issuer) {
+          tma_store_wait_all0();   // stores complete (not only read): the staging smem is free, the data is out
+          if (first) stamp(round, 4);
+        }
       }
       // ---- end of tile: TMEM drained, staging smem free, every role done
       tc_fence_before();
@@ -391,6 +416,7 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
       if (threadIdx.x == 0) {
         ++barriers_done;
         const unsigned target = barriers_done * gridDim.x;
+        stamp(round, 5);
         asm volatile("fence.proxy.async;" ::: "memory");
         __threadfence();
         atomicAdd(grid_counter, 1u);
@@ -401,6 +427,7 @@ w2_chain_kernel(const W2Round* __restrict__ rounds, int r0, int r1, unsigned* __
         }
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
+        stamp(round, 6);
       }
       __syncthreads();
     }
@@ -704,6 +731,7 @@ int W2Engine::init(void* ws, size_t bytes, const int n_per_layer[5]) {
   d_layers = (W2Layer*)take(sizeof(W2Layer) * 5);
   d_maps = (CUtensorMap*)take(sizeof(CUtensorMap) * MAX_MAPS);
   d_grid_counter = (unsigned*)take(256);
+  d_trace = (unsigned long long*)take(W2_TRACE_WORDS * 8);
 
   // ---- build the round lists once (pointers are stable)
   Builder b;
@@ -803,7 +831,7 @@ int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
   if (!chain) {
     for (int r = r0; r < r1; ++r) {
       const int grid = rounds[r].n_tiles < sms ? rounds[r].n_tiles : sms;
-      w2_chain_kernel<<<grid, T_THREADS, T_SMEM_BYTES, s>>>(d_rounds, r, r + 1, d_grid_counter);
+      w2_chain_kernel<<<grid, T_THREADS, T_SMEM_BYTES, s>>>(d_rounds, r, r + 1, d_grid_counter, nullptr);
     }
     STB_CUDA_CHECK(cudaGetLastError());
     return STB_OK;
@@ -823,7 +851,9 @@ int W2Engine::run_rounds(int r0, int r1, cudaStream_t s) {
   cfg.numAttrs = 1;
   const W2Round* dr = d_rounds;
   unsigned* ctr = d_grid_counter;
-  STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, w2_chain_kernel, dr, r0, r1, ctr));
+  static const bool tracing = [] { const char* e = getenv("STB_W2_TRACE"); return e && e[0] == '1'; }();
+  unsigned long long* tr = tracing ? d_trace : nullptr;
+  STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, w2_chain_kernel, dr, r0, r1, ctr, tr));
   return STB_OK;
 }
 
