@@ -228,7 +228,10 @@ def run_native(args, rank, local_rank, world):
     cimg_full = O.to_tensor(content).to(dev)
     simg = O.to_tensor(style).to(dev)
     sband = D.make_band(size, rank, world) if world > 1 else None
-    m.ensure_workspace([(h_loc, size), (sband.h_local if sband is not None else size, size)])
+    ws_sizes = [(h_loc, size), (sband.h_local if sband is not None else size, size)]
+    if band is not None:   # mailboxes + (halo mode) the peer-mapped workspace, before anything touches the workspace
+        st._ensure_peer_memory(ws_sizes, max(b.h_local for b in D.all_bands(size, world)), size)
+    m.ensure_workspace(ws_sizes)
     means, srms = st._style_stats(simg, size, size)   # tiled over the ranks like the iterate when world > 1
     cimg = cimg_full
     if band is not None:
@@ -237,7 +240,7 @@ def run_native(args, rank, local_rank, world):
     ct = m.content_features(cimg)
     m.set_targets(h_loc, size, ct, 0.015, means, srms, st.style_weights, 2.0)
     if band is not None:
-        st._setup_comm(band, size, max(b.h_local for b in D.all_bands(size, world)), size)
+        st._setup_comm(band, size)
     st.image = cimg.clone()
     st.average = stb.style_transfer.EMA(st.image, 0.99)
     ea, eas = torch.zeros_like(st.image), torch.zeros_like(st.image)
@@ -331,19 +334,16 @@ def run_native(args, rank, local_rank, world):
             torch.cuda.empty_cache()
         barrier()
 
-    # ---- instrumented pass: per-kernel-class device time (events around every launch)
+    # ---- instrumented pass: per-kernel-class device time (events around every launch; graphs off while profiling).
+    # Tiled: every rank iterates (the exchanges need all of them), rank 0 records.
     prof = None
+    n_prof = min(args.steps, 10)
     if rank == 0:
         _lib.check(m.lib.stb_profile_enable(m.ctx, 1))
-        n_prof = min(args.steps, 10)
-        g_prof = grad if grad is not None else torch.empty_like(st.image)
-        for _ in range(n_prof):
-            if band is None:
-                one_iteration()
-            else:  # instrumented compute only (no exchanges inside the event spans' critical path on rank 0)
-                m.iterate_fwd(st.image)
-                m.iterate_bwd(st.image, g_prof, st._loss_host)
-        torch.cuda.synchronize()
+    for _ in range(n_prof):
+        one_iteration()
+    torch.cuda.synchronize()
+    if rank == 0:
         ms = (ctypes.c_float * 10)()
         cnt = (ctypes.c_int * 10)()
         _lib.check(m.lib.stb_profile_read(m.ctx, ms, cnt, 10))
@@ -415,8 +415,10 @@ def run_native(args, rank, local_rank, world):
         if tiled:
             par = (f'{world}-way spatial tiling: bands of {band.own_rows}+{band.top_apron + band.bottom_apron} halo rows '
                    f'(rank 0); exchanges = ' +
-                   ('peer-memory kernels inside the iteration graph (stats all-reduce, seam reduce fused with Adam, '
-                    'halo pull; CUDA IPC over NVLink)' if st._comm_mode == 'peer' else
+                   ((f'peer-memory kernels inside the iteration graph, tile mode {st._tile_mode} '
+                     '(halo: own rows only + one boundary-row pull per layer; apron: 80 recomputed rows per side) '
+                     '+ stats all-reduce, Adam on own rows, image halo pull; CUDA IPC over NVLink')
+                    if st._comm_mode == 'peer' else
                     'host-driven NCCL (1 all-reduce + 2 send/recv per iteration)'))
         line = dict(metric='stylize iterations/sec at end_scale=2048', value=value, unit='it/s', n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3, PARITY_ITS), ms_per_step=ms_per_step,

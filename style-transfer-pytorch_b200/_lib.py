@@ -53,6 +53,10 @@ def _declare(lib):
         'stb_comm_connect_ipc': [vp, vp],
         'stb_comm_connect_local': [vp, pp],
         'stb_comm_disconnect': [vp],
+        'stb_comm_alloc_workspace': [vp, sz, vp, pp, vp],
+        'stb_comm_connect_ws_ipc': [vp, vp],
+        'stb_comm_connect_ws_local': [vp, pp],
+        'stb_comm_release_workspace': [vp, i],
         'stb_comm_set_geometry': [vp, i, i, i, i, i, i, i],
         'stb_comm_reset': [vp, vp],
         'stb_iterate_banded': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, vp, vp],
@@ -92,7 +96,8 @@ EXPORTS = [
     'stb_last_error', 'stb_ctx_create', 'stb_ctx_destroy', 'stb_workspace_bytes', 'stb_bind_workspace',
     'stb_style_stats', 'stb_content_features', 'stb_set_targets', 'stb_iterate', 'stb_iterate_ex',
     'stb_set_band', 'stb_stats_block', 'stb_iterate_fwd', 'stb_iterate_bwd', 'stb_adam_update',
-    'stb_set_loss_ring', 'stb_resize', 'stb_comm_create', 'stb_comm_connect_ipc', 'stb_comm_connect_local', 'stb_comm_disconnect',
+    'stb_set_loss_ring', 'stb_resize', 'stb_comm_create', 'stb_comm_connect_ipc', 'stb_comm_connect_local', 'stb_comm_disconnect', 'stb_comm_alloc_workspace',
+    'stb_comm_connect_ws_ipc', 'stb_comm_connect_ws_local', 'stb_comm_release_workspace',
     'stb_comm_set_geometry', 'stb_comm_reset',
     'stb_iterate_banded', 'stb_graph_status', 'stb_launch_count', 'stb_profile_enable', 'stb_profile_read', 'stb_debug_activation', 'stb_debug_w2_trace',
 ]

@@ -129,6 +129,12 @@ struct stb_ctx {
   void* comm_mailbox = nullptr;       // own cudaMalloc block
   size_t comm_bytes = 0;
   int comm_max_h = 0, comm_max_w = 0;
+  // per-layer-halo mode: the workspace itself is a cudaMalloc block of the library, mapped by the neighbours (they pull
+  // single boundary rows of the activation / gradient tensors out of it)
+  void* shared_ws = nullptr;
+  size_t shared_ws_bytes = 0;
+  bool shared_ws_ipc = false, halo_mode = false;
+  int halo_seq = 0;                   // exchange counter inside the iteration being recorded
 };
 
 // every ctx entry point runs on the context's device, whatever the caller's current device is
@@ -215,8 +221,48 @@ BandRows band_rows(const stb_ctx* ctx, const Plan& pl, int conv) {
   return b;
 }
 
-// forward through conv `last_conv` (inclusive); do_tv also produces the TV gradient / loss partials
-int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool do_tv, cudaStream_t s) {
+// ---- per-layer halo exchange ("halo mode" of a tiled iteration).  A band computes only its own
+// rows of every activation / gradient tensor; the row above and the row below them, which the next 3x3 kernel reads,
+// are the neighbours' boundary own rows and are pulled straight out of the neighbours' workspaces.
+struct HaloPlans { Plan up, dn; };
+int level_of(int conv) {
+  int level = 0;
+  for (int i = 0; i < conv; ++i)
+    if (kPoolAfter[i]) ++level;
+  return level;
+}
+// tensor with C channels at pyramid level `level` (width w_l); off_* = its byte offset in the plan of me / up / down.
+// sync_only: publish + wait the stamps without copying (a buffer the neighbours pulled from is about to be rewritten).
+int halo_exchange(stb_ctx* ctx, const Plan& pl, int level, int w_l, int C, size_t off_me, size_t off_up, size_t off_dn,
+                  bool sync_only, cudaStream_t s) {
+  const CommDev& c = ctx->comm;
+  const bool has_up = c.rank > 0, has_dn = c.rank + 1 < c.world;
+  const size_t row_bytes = (size_t)w_l * C * 2;
+  const int o0 = ctx->band_own0 >> level, r = ctx->band_own_rows >> level;   // interior edges: multiples of 16
+  HaloRowArgs a{};
+  a.row_bytes = sync_only ? 0 : row_bytes;
+  a.seq = ++ctx->halo_seq;
+  STB_CHECK(a.seq < 256, STB_ERR_STATE, "too many halo exchanges in one iteration");
+  if (has_up) {
+    const int up_own0 = (c.rank - 1 > 0 ? COMM_APRON : 0) >> level;
+    const int up_last = (c.up_apron_row0 >> level) - 1;   // last own row of the upper band at this level
+    STB_CHECK(c.ws[c.rank - 1] != nullptr && up_last >= up_own0 && o0 >= 1, STB_ERR_STATE, "halo: upper neighbour not mapped");
+    a.src_up = c.ws[c.rank - 1] + off_up + (size_t)up_last * row_bytes;
+    a.dst_up = ctx->ws + off_me + (size_t)(o0 - 1) * row_bytes;
+  }
+  if (has_dn) {
+    STB_CHECK(c.ws[c.rank + 1] != nullptr, STB_ERR_STATE, "halo: lower neighbour not mapped");
+    a.src_dn = c.ws[c.rank + 1] + off_dn + (size_t)(COMM_APRON >> level) * row_bytes;
+    a.dst_dn = ctx->ws + off_me + (size_t)(o0 + r) * row_bytes;
+  }
+  (void)pl;
+  return launch_halo_rows(c, a, s);
+}
+
+// forward through conv `last_conv` (inclusive); do_tv also produces the TV gradient / loss partials.
+// halo != nullptr: per-layer-halo mode of a tiled iteration (own rows only + one exchange per layer).
+int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool do_tv, cudaStream_t s,
+            const HaloPlans* halo = nullptr) {
   int ntv = 0;
   ctx->prof.begin(PC_CONV0_FWD, s);
   if (do_tv) {
@@ -235,14 +281,23 @@ int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool 
     a.H = pl.h[i]; a.W = pl.w[i]; a.Cin = kCin[i]; a.Cout = kCout[i]; a.mode = 0;
     a.A = cur; a.Bw = ctx->wf[i]; a.out = at<bf16>(ctx, pl.act_off[i]); a.bias = ctx->bias[i];
     cur = a.out;
+    size_t x_me = pl.act_off[i], x_up = 0, x_dn = 0;   // the tensor the next conv reads, for the halo exchange
+    int x_level = level_of(i), x_w = pl.w[i];
+    if (halo) { x_up = halo->up.act_off[i]; x_dn = halo->dn.act_off[i]; }
     if (kPoolAfter[i] && i < last_conv) {  // the 2x2 pool that follows this conv is produced by its epilogue
+      if (halo) { x_me = pl.pool_off[np]; x_up = halo->up.pool_off[np]; x_dn = halo->dn.pool_off[np]; ++x_level; x_w = pl.w[i + 1]; }
       a.pool_out = at<bf16>(ctx, pl.pool_off[np++]);
       a.pooling = ctx->pooling;
       cur = a.pool_out;
     }
+    if (halo) {  // own rows only (conv0 ran on the whole local image: its halo rows are already there)
+      const BandRows br = band_rows(ctx, pl, i);
+      a.y_origin = br.own0; a.y_rows = br.rows;
+    }
     ctx->prof.begin(PC_CONV_FWD, s);
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
+    if (halo && i < last_conv) STB_TRY(halo_exchange(ctx, pl, x_level, x_w, kCout[i], x_me, x_up, x_dn, false, s));
   }
   return STB_OK;
 }
@@ -369,8 +424,22 @@ void comm_release(stb_ctx* ctx) {
       if (r != ctx->comm.rank && ctx->comm.mbox[r]) cudaIpcCloseMemHandle(ctx->comm.mbox[r]);
   if (ctx->comm_mailbox) cudaFree(ctx->comm_mailbox);
   ctx->comm_mailbox = nullptr;
+  uint8_t* keep_ws[COMM_MAX_RANKS];
+  std::memcpy(keep_ws, ctx->comm.ws, sizeof(keep_ws));
   ctx->comm = CommDev{};
+  std::memcpy(ctx->comm.ws, keep_ws, sizeof(keep_ws));   // the shared workspace outlives a mailbox re-creation
   ctx->comm_ready = ctx->comm_geometry = ctx->comm_ipc = false;
+}
+void shared_ws_release(stb_ctx* ctx) {
+  if (ctx->shared_ws_ipc)
+    for (int r = 0; r < COMM_MAX_RANKS; ++r)
+      if (ctx->comm.ws[r] && ctx->comm.ws[r] != ctx->shared_ws) cudaIpcCloseMemHandle(ctx->comm.ws[r]);
+  for (int r = 0; r < COMM_MAX_RANKS; ++r) ctx->comm.ws[r] = nullptr;
+  if (ctx->shared_ws) {
+    if (ctx->ws == ctx->shared_ws) { ctx->ws = nullptr; ctx->ws_bytes = 0; ctx->w2_ready = false; ctx->targets_set = false; }
+    cudaFree(ctx->shared_ws);
+  }
+  ctx->shared_ws = nullptr; ctx->shared_ws_bytes = 0; ctx->shared_ws_ipc = false;
 }
 }  // namespace
 
@@ -438,6 +507,7 @@ int stb_ctx_create(int device, int pooling, const float* const* conv_w, const fl
 void stb_ctx_destroy(stb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  shared_ws_release(ctx);
   comm_release(ctx);
   if (ctx->owned) cudaFree(ctx->owned);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -557,8 +627,8 @@ int stb_set_targets(stb_ctx* ctx, int H, int W, const void* content_target_bf16,
 namespace {
 
 // phase 1: forward + this context's (band-local) statistics into the stats block
-int iterate_fwd(stb_ctx* ctx, const Plan& pl, const float* img, cudaStream_t s) {
-  STB_TRY(forward(ctx, pl, img, NCONV - 1, true, s));
+int iterate_fwd(stb_ctx* ctx, const Plan& pl, const float* img, cudaStream_t s, const HaloPlans* halo = nullptr) {
+  STB_TRY(forward(ctx, pl, img, NCONV - 1, true, s, halo));
   STB_TRY(style_grams(ctx, pl, s));
   const BandRows b22 = band_rows(ctx, pl, kContentConv);
   const size_t off22 = (size_t)b22.own0 * pl.w[kContentConv] * 512;
@@ -576,7 +646,8 @@ int iterate_fwd(stb_ctx* ctx, const Plan& pl, const float* img, cudaStream_t s) 
 
 // phase 2: W2 losses on the (globally reduced) statistics, backward to the image, optional fused update
 int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
-                const AdamScalars* d_adam, int apply_update, float* grad_out, float* loss_out_host8, cudaStream_t s) {
+                const AdamScalars* d_adam, int apply_update, float* grad_out, float* loss_out_host8, cudaStream_t s,
+                const HaloPlans* halo = nullptr) {
   const int H = pl.H, W = pl.W;
   const long n22 = (long)band_rows(ctx, pl, kContentConv).h_global * pl.w[kContentConv] * 512;  // global numel
   float* loss_dev = at<float>(ctx, pl.loss_off);
@@ -605,15 +676,21 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
     a.a2_row0 = br.own0; a.a2_rows = br.rows; a.row_lo = br.own0; a.row_hi = br.own0 + br.rows;
     a.B2 = L.gs_bf16; a.bias = L.gmu_bias;
     a.mask_src = at<bf16>(ctx, pl.act_off[12]); a.out = g[cur];
+    if (halo) { a.y_origin = br.own0; a.y_rows = br.rows; }
     ctx->prof.begin(PC_CONV_BWD, s);
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
+    if (halo)
+      STB_TRY(halo_exchange(ctx, pl, level_of(12), pl.w[12], 512, pl.g_off[cur], halo->up.g_off[cur], halo->dn.g_off[cur],
+                            false, s));
   }
   for (int i = NCONV - 1; i >= 1; --i) {
     // g[cur] = gradient w.r.t. conv i pre-activation, [h_i][w_i][Cout_i]; produce gradient for conv i-1
     PixelGemmArgs a;
     a.H = pl.h[i]; a.W = pl.w[i]; a.Cin = kCout[i]; a.Cout = kCin[i];
     a.A = g[cur]; a.Bw = ctx->wb[i]; a.out = g[cur ^ 1];
+    const BandRows bi = band_rows(ctx, pl, i);
+    if (halo) { a.y_origin = bi.own0; a.y_rows = bi.rows; }
     if (kPoolAfter[i - 1]) {
       a.mode = 2;
       ctx->prof.begin(PC_CONV_BWD, s);
@@ -621,10 +698,24 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
       ctx->prof.end(s);
       cur ^= 1;
       ctx->prof.begin(PC_POOL_BWD, s);
-      STB_TRY(launch_pool_bwd(ctx->pooling, g[cur], at<bf16>(ctx, pl.act_off[i - 1]), g[cur ^ 1], pl.h[i - 1],
-                              pl.w[i - 1], kCout[i - 1], s));
+      if (!halo) {
+        STB_TRY(launch_pool_bwd(ctx->pooling, g[cur], at<bf16>(ctx, pl.act_off[i - 1]), g[cur ^ 1], pl.h[i - 1],
+                                pl.w[i - 1], kCout[i - 1], s));
+      } else {
+        // g[cur ^ 1] is the buffer the neighbours pulled their halo rows from one exchange ago: make sure they are done
+        STB_TRY(halo_exchange(ctx, pl, level_of(i), pl.w[i], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
+                              halo->dn.g_off[cur], true, s));
+        const BandRows bp = band_rows(ctx, pl, i - 1);   // own rows before the pool
+        const int C = kCout[i - 1];
+        STB_TRY(launch_pool_bwd(ctx->pooling, g[cur] + (size_t)bi.own0 * pl.w[i] * C,
+                                at<bf16>(ctx, pl.act_off[i - 1]) + (size_t)bp.own0 * pl.w[i - 1] * C,
+                                g[cur ^ 1] + (size_t)bp.own0 * pl.w[i - 1] * C, bp.rows, pl.w[i - 1], C, s));
+      }
       ctx->prof.end(s);
       cur ^= 1;
+      if (halo)
+        STB_TRY(halo_exchange(ctx, pl, level_of(i - 1), pl.w[i - 1], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
+                              halo->dn.g_off[cur], false, s));
     } else {
       a.mode = 1;
       a.mask_src = at<bf16>(ctx, pl.act_off[i - 1]);
@@ -646,6 +737,9 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
       STB_TRY(launch_pixel_gemm(a, s));
       ctx->prof.end(s);
       cur ^= 1;
+      if (halo)
+        STB_TRY(halo_exchange(ctx, pl, level_of(i - 1), pl.w[i - 1], kCin[i], pl.g_off[cur], halo->up.g_off[cur],
+                              halo->dn.g_off[cur], false, s));
     }
   }
   // conv0 backward: interior pixels on the tensor cores (1x1 GEMM + col2im) with the optimiser step as epilogue;
@@ -952,6 +1046,84 @@ int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes) {
   return STB_OK;
 }
 
+// ---- per-layer-halo mode: the workspace is a cudaMalloc block of the library that the neighbours map (CUDA IPC) and
+// pull single boundary rows from.  stb_comm_alloc_workspace allocates + zeroes + binds it (like stb_bind_workspace);
+// stb_comm_connect_ws_* hands in every rank's handle / pointer (rank order; only the neighbours are mapped) and switches
+// stb_iterate_banded to "own rows only + one row exchange per layer".  Without it the 80-row aprons are recomputed.
+int stb_comm_alloc_workspace(stb_ctx* ctx, size_t bytes, void* ipc_handle_out64, void** ptr_out, void* stream) {
+  STB_ENTER(ctx);
+  STB_CHECK(bytes >= ctx->w2_bytes + 4096, STB_ERR_WORKSPACE, "workspace smaller than the fixed W2 block");
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->halo_mode = false;
+  shared_ws_release(ctx);
+  STB_CUDA_CHECK(cudaMalloc(&ctx->shared_ws, bytes));
+  STB_CUDA_CHECK(cudaMemset(ctx->shared_ws, 0, bytes));   // rows a band never computes are read by nobody, but stay finite
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->shared_ws_bytes = bytes;
+  if (ipc_handle_out64) {
+    cudaIpcMemHandle_t h;
+    STB_CUDA_CHECK(cudaIpcGetMemHandle(&h, ctx->shared_ws));
+    std::memcpy(ipc_handle_out64, &h, sizeof(h));
+  }
+  if (ptr_out) *ptr_out = ctx->shared_ws;
+  return stb_bind_workspace(ctx, ctx->shared_ws, bytes, stream);
+}
+
+static int connect_ws(stb_ctx* ctx, const void* handles, void* const* pointers) {
+  STB_CHECK(ctx->shared_ws && ctx->comm_mailbox, STB_ERR_STATE, "stb_comm_create + stb_comm_alloc_workspace first");
+  const int rank = ctx->comm.rank, world = ctx->comm.world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ctx->comm.ws[r] = static_cast<uint8_t*>(ctx->shared_ws); continue; }
+    if (r != rank - 1 && r != rank + 1) continue;   // only the neighbours' rows are ever read
+    void* p = nullptr;
+    if (handles) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * r, sizeof(h));
+      STB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    } else {
+      p = pointers[r];
+      STB_CHECK(p != nullptr, STB_ERR_INVALID, "null workspace pointer of rank %d", r);
+      cudaPointerAttributes pa;
+      STB_CUDA_CHECK(cudaPointerGetAttributes(&pa, p));
+      if (pa.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else STB_CUDA_CHECK(e);
+      }
+    }
+    ctx->comm.ws[r] = static_cast<uint8_t*>(p);
+  }
+  ctx->shared_ws_ipc = handles != nullptr;
+  ctx->halo_mode = true;
+  ctx->reset_graphs();
+  return STB_OK;
+}
+int stb_comm_connect_ws_ipc(stb_ctx* ctx, const void* handles) {
+  STB_ENTER(ctx);
+  STB_CHECK(handles != nullptr, STB_ERR_INVALID, "null handles");
+  return connect_ws(ctx, handles, nullptr);
+}
+int stb_comm_connect_ws_local(stb_ctx* ctx, void* const* pointers) {
+  STB_ENTER(ctx);
+  STB_CHECK(pointers != nullptr, STB_ERR_INVALID, "null pointers");
+  return connect_ws(ctx, nullptr, pointers);
+}
+// drop the shared workspace and its mappings (the host barriers before any rank frees memory a neighbour still maps)
+int stb_comm_release_workspace(stb_ctx* ctx, int unmap_only) {
+  STB_ENTER(ctx);
+  STB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->reset_graphs();
+  ctx->halo_mode = false;
+  if (unmap_only) {
+    if (ctx->shared_ws_ipc)
+      for (int r = 0; r < COMM_MAX_RANKS; ++r)
+        if (ctx->comm.ws[r] && ctx->comm.ws[r] != ctx->shared_ws) { cudaIpcCloseMemHandle(ctx->comm.ws[r]); ctx->comm.ws[r] = nullptr; }
+    return STB_OK;
+  }
+  shared_ws_release(ctx);
+  return STB_OK;
+}
+
 // unmap the peers' mailboxes (before any rank frees / re-creates its own; the host barriers in between)
 int stb_comm_disconnect(stb_ctx* ctx) {
   STB_ENTER(ctx);
@@ -1021,15 +1193,26 @@ int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_
   }
   ctx->dev_step_mirror = step;
   float* grad = reinterpret_cast<float*>(c.mbox[c.rank] + c.off_grad);
+  // per-layer-halo mode: the neighbours' buffers sit at the offsets of THEIR plans (edge bands have one apron less)
+  HaloPlans hp;
+  const HaloPlans* halo = nullptr;
+  if (ctx->halo_mode) {
+    STB_CHECK(ctx->ws == ctx->shared_ws && ctx->shared_ws != nullptr, STB_ERR_STATE,
+              "halo mode needs the library-owned workspace bound (stb_comm_alloc_workspace)");
+    make_plan(ctx, c.rank > 0 ? c.up_h_local : pl.H, pl.W, &hp.up);
+    make_plan(ctx, c.rank + 1 < c.world ? c.dn_h_local : pl.H, pl.W, &hp.dn);
+    halo = &hp;
+  }
   auto run = [&]() -> int {
+    ctx->halo_seq = 0;
     STB_TRY(launch_comm_phase(c, 0, s));
     STB_TRY(launch_halo_pull(c, img, s));
-    STB_TRY(iterate_fwd(ctx, pl, img, s));
+    STB_TRY(iterate_fwd(ctx, pl, img, s, halo));
     STB_TRY(launch_stats_allreduce(c, at<float>(ctx, pl.stats_off), pl.stats_floats, s));
     adam_scalars_kernel<<<1, 1, 0, s>>>(ctx->d_step, ctx->d_adam, lr, beta1, beta2, adam_eps, ema_decay);
-    STB_TRY(iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad, loss_out_host8, s));
+    STB_TRY(iterate_bwd(ctx, pl, img, nullptr, nullptr, nullptr, nullptr, 0, grad, loss_out_host8, s, halo));
     STB_TRY(launch_comm_phase(c, 2, s));
-    STB_TRY(launch_adam_seam(c, img, exp_avg, exp_avg_sq, ema, ctx->d_adam, s));
+    STB_TRY(launch_adam_seam(c, img, exp_avg, exp_avg_sq, ema, ctx->d_adam, halo ? 0 : 1, s));
     return launch_comm_phase(c, 3, s);
   };
   stb_ctx::GraphKey key{};

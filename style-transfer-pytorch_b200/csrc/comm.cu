@@ -150,16 +150,49 @@ __global__ void __launch_bounds__(256) stats_allreduce_kernel(CommDev c, float* 
 
 // own rows: g = grad_local (+ upper neighbour's bottom-apron rows) (+ lower neighbour's top-apron rows); Adam; clamp;
 // EMA; the first / last APRON updated rows also go to the outboxes (the neighbours' next halo)
+// Per-layer halo exchange ("halo mode"): the band computed only its own rows of a tensor; the one
+// row above / below them that the next 3x3 kernel reads is the neighbour's boundary own row, pulled here.  One kernel =
+// publish my progress stamp (everything before it on this stream is done: kernel boundary + system fence), wait for the
+// neighbours' same stamp, copy.  Few small CTAs: a waiting rank leaves the GPU to whoever shares it.
+__global__ void __launch_bounds__(256) halo_rows_kernel(CommDev c, HaloRowArgs a) {
+  unsigned long long* own = reinterpret_cast<unsigned long long*>(c.mbox[c.rank]);
+  const unsigned long long want = own[COMM_ITER] * 256ull + (unsigned long long)a.seq;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(own + COMM_PROG, want);
+    }
+    if (a.src_up != nullptr)
+      wait_stamp(reinterpret_cast<const unsigned long long*>(c.mbox[c.rank - 1]) + COMM_PROG, want, own + COMM_ERR,
+                 c.timeout_ns);
+    if (a.src_dn != nullptr)
+      wait_stamp(reinterpret_cast<const unsigned long long*>(c.mbox[c.rank + 1]) + COMM_PROG, want, own + COMM_ERR,
+                 c.timeout_ns);
+  }
+  __syncthreads();
+  const long n16 = (long)(a.row_bytes >> 4);
+  const int sides = (a.src_up != nullptr ? 1 : 0) + (a.src_dn != nullptr ? 1 : 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16 * sides; i += (long)gridDim.x * blockDim.x) {
+    int side = (int)(i / n16);
+    const long e = i - side * n16;
+    if (a.src_up == nullptr) side = 1;
+    const float4* src = reinterpret_cast<const float4*>(side == 0 ? a.src_up : a.src_dn) + e;
+    float4* dst = reinterpret_cast<float4*>(side == 0 ? a.dst_up : a.dst_dn) + e;
+    *dst = ld_peer(src);
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256)
 adam_seam_kernel(CommDev c, float* __restrict__ img, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                 float* __restrict__ ema, const AdamScalars* __restrict__ d_adam) {
+                 float* __restrict__ ema, const AdamScalars* __restrict__ d_adam, int add_seams) {
   typedef typename Vec<V>::T T;
   const AdamScalars ac = *d_adam;
   const int w4 = c.W / V;
   const long per = (long)c.own_rows * w4;
   const T* grad = reinterpret_cast<const T*>(c.mbox[c.rank] + c.off_grad);
-  const bool has_up = c.rank > 0, has_dn = c.rank + 1 < c.world;
+  // add_seams = 0 (per-layer-halo mode): the local gradient of the own rows is already complete
+  const bool has_up = c.rank > 0 && add_seams, has_dn = c.rank + 1 < c.world && add_seams;
   const T* gup = has_up ? reinterpret_cast<const T*>(c.mbox[c.rank - 1] + c.off_grad) : nullptr;
   const T* gdn = has_dn ? reinterpret_cast<const T*>(c.mbox[c.rank + 1] + c.off_grad) : nullptr;
   T* out_first = reinterpret_cast<T*>(c.mbox[c.rank] + c.off_outbox[0]);
@@ -235,6 +268,7 @@ int comm_preload() {
   STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, stats_allreduce_kernel));
   STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, adam_seam_kernel<4>));
   STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, adam_seam_kernel<1>));
+  STB_CUDA_CHECK(cudaFuncGetAttributes(&fa, halo_rows_kernel));
   return STB_OK;
 }
 
@@ -262,12 +296,24 @@ int launch_stats_allreduce(const CommDev& c, float* stats, size_t n_floats, cuda
   return STB_OK;
 }
 
+int launch_halo_rows(const CommDev& c, const HaloRowArgs& a, cudaStream_t s) {
+  STB_CHECK(a.row_bytes % 16 == 0, STB_ERR_INVALID, "halo row of %zu bytes", a.row_bytes);   // 0: stamps only
+  if (a.src_up == nullptr && a.src_dn == nullptr) return STB_OK;
+  long blocks = (long)(a.row_bytes / 16) * 2 / 256 + 1;
+  if (blocks > 16) blocks = 16;
+  halo_rows_kernel<<<(int)blocks, 256, 0, s>>>(c, a);
+  STB_CUDA_CHECK(cudaGetLastError());
+  return STB_OK;
+}
+
 int launch_adam_seam(const CommDev& c, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
-                     const AdamScalars* d_adam, cudaStream_t s) {
+                     const AdamScalars* d_adam, int add_seams, cudaStream_t s) {
   if (c.W % 4 == 0)
-    adam_seam_kernel<4><<<grid_for(3l * c.own_rows * (c.W / 4)), 256, 0, s>>>(c, img, exp_avg, exp_avg_sq, ema, d_adam);
+    adam_seam_kernel<4><<<grid_for(3l * c.own_rows * (c.W / 4)), 256, 0, s>>>(c, img, exp_avg, exp_avg_sq, ema, d_adam,
+                                                                             add_seams);
   else
-    adam_seam_kernel<1><<<grid_for(3l * c.own_rows * c.W), 256, 0, s>>>(c, img, exp_avg, exp_avg_sq, ema, d_adam);
+    adam_seam_kernel<1><<<grid_for(3l * c.own_rows * c.W), 256, 0, s>>>(c, img, exp_avg, exp_avg_sq, ema, d_adam,
+                                                                        add_seams);
   STB_CUDA_CHECK(cudaGetLastError());
   return STB_OK;
 }

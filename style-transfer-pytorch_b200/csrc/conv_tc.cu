@@ -71,6 +71,7 @@ struct KParams {
   int row_lo, row_hi;
   int pooling;  // MODE 0: -1 = none, else STB_POOL_*: also emit the 2x2-pooled output (tmPool)
   int mma_interleave;  // issue order of the MT sub-tiles' MMAs (see the issuer loop)
+  int y_origin;        // first output row of the tile grid (row window of a band that computes its own rows only)
 };
 
 template <int BN, int MODE>
@@ -133,7 +134,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tn = tile % p.n_tiles_n;
         const int t2 = tile / p.n_tiles_n;
         const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-        const int y0 = ty * TILE_H, x0 = tx * TILE_W * C::MT, n0 = tn * BN;
+        const int y0 = p.y_origin + ty * TILE_H, x0 = tx * TILE_W * C::MT, n0 = tn * BN;
         for (int c = 0; c < n_chunks; ++c) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(&a_empty[sa], pa ^ 1);
@@ -257,7 +258,7 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tn = tile % p.n_tiles_n;
       const int t2 = tile / p.n_tiles_n;
       const int tx = t2 % p.tiles_x, ty = t2 / p.tiles_x;
-      const int y0 = ty * TILE_H, n0 = tn * BN;
+      const int y0 = p.y_origin + ty * TILE_H, n0 = tn * BN;
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
@@ -445,7 +446,13 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   const int MT = BN == 256 ? 1 : 2;  // must match Cfg<BN>::MT
   const int tile_w = TILE_W * MT;
   kp.tiles_x = (a.W + tile_w - 1) / tile_w;
-  kp.tiles_y = (a.H + TILE_H - 1) / TILE_H;
+  // row window [y_origin, y_origin + y_rows): a band in per-layer-halo mode computes its own rows only
+  const int y_rows = a.y_rows > 0 ? a.y_rows : a.H - a.y_origin;
+  STB_CHECK(a.y_origin >= 0 && y_rows > 0 && a.y_origin + y_rows <= a.H, STB_ERR_INVALID,
+            "pixel_gemm: row window %d+%d of %d", a.y_origin, y_rows, a.H);
+  STB_CHECK(a.pool_out == nullptr || a.y_origin % 2 == 0, STB_ERR_INVALID, "pixel_gemm: fused pool needs an even row origin");
+  kp.y_origin = a.y_origin;
+  kp.tiles_y = (y_rows + TILE_H - 1) / TILE_H;
   kp.n_tiles_n = a.Cout / BN;
   kp.total_tiles = kp.tiles_x * kp.tiles_y * kp.n_tiles_n;
   kp.a2_row0 = a.a2_row0;

@@ -34,6 +34,7 @@ struct PixelGemmArgs {
   const bf16* ctarget = nullptr;  // bwd, optional: [H][W][Cout]
   float cscale = 0.f;
   int row_lo = 0, row_hi = 1 << 30;  // rows where bias (bwd) / content term apply
+  int y_origin = 0, y_rows = 0;   // output row window (0 rows = all): tiles start at y_origin, inputs outside are halo rows
   bf16* pool_out = nullptr;       // fwd, optional: [H/2][W/2][Cout], the 2x2/stride-2 pool of `out` (floor mode)
   int pooling = -1;               // STB_POOL_* of pool_out
 };
@@ -143,13 +144,14 @@ struct W2Engine {
 constexpr int COMM_APRON = 80;       // halo rows on each interior side of a band (receptive-field radius of relu5_1)
 constexpr int COMM_MAX_RANKS = 8;
 // u64 slots at the head of a mailbox (one 128-byte line each)
-enum { COMM_ITER = 0, COMM_FLAG_STATS = 16, COMM_FLAG_GRAD = 32, COMM_FLAG_HALO = 48, COMM_ERR = 64 };
+enum { COMM_ITER = 0, COMM_FLAG_STATS = 16, COMM_FLAG_GRAD = 32, COMM_FLAG_HALO = 48, COMM_ERR = 64, COMM_PROG = 80 };
 struct CommDev {  // passed by value to the exchange kernels
   int rank, world;
   uint8_t* mbox[COMM_MAX_RANKS];   // mailbox of every rank as mapped into THIS process (own one included)
   size_t off_stats[2], off_grad, off_outbox[2];
   int W, h_local, own0, own_rows;           // this band: local image height, first own row, number of own rows
   int up_h_local, up_apron_row0, dn_h_local;  // neighbours' local heights; first bottom-apron row of the upper band
+  uint8_t* ws[COMM_MAX_RANKS];                // per-layer-halo mode: every rank's WORKSPACE as mapped here (else null)
   unsigned long long timeout_ns;              // a peer wait longer than this traps instead of hanging
 };
 size_t comm_mailbox_bytes(size_t stats_floats, int max_h_local, int max_W, size_t off[5]);
@@ -157,7 +159,19 @@ int launch_comm_phase(const CommDev& c, int phase, cudaStream_t s);   // 0 begin
 int launch_halo_pull(const CommDev& c, float* img, cudaStream_t s);
 int launch_stats_allreduce(const CommDev& c, float* stats, size_t n_floats, cudaStream_t s);
 int launch_adam_seam(const CommDev& c, float* img, float* exp_avg, float* exp_avg_sq, float* ema,
-                     const AdamScalars* d_adam, cudaStream_t s);
+                     const AdamScalars* d_adam, int add_seams, cudaStream_t s);
+// per-layer halo exchange: publish progress stamp `seq` of this iteration, wait for the neighbours' same stamp, then copy
+// one boundary row (row_bytes) from each neighbour's buffer into this rank's halo rows.  Pointers are absolute (peer
+// workspaces are mapped); a null source / destination skips that side.
+struct HaloRowArgs {
+  const uint8_t* src_up;   // upper neighbour's LAST own row of the tensor
+  uint8_t* dst_up;         // my row just above my first own row
+  const uint8_t* src_dn;   // lower neighbour's FIRST own row
+  uint8_t* dst_dn;         // my row just below my last own row
+  size_t row_bytes;
+  int seq;
+};
+int launch_halo_rows(const CommDev& c, const HaloRowArgs& a, cudaStream_t s);
 
 // force every kernel of the library into the context (lazy module loading may otherwise synchronise the context at
 // a first launch, which deadlocks against a resident peer-wait kernel)

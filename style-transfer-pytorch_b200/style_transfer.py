@@ -125,6 +125,7 @@ class NativeVGG:
                                                ctypes.byref(self.ctx)))
         self._ws = None
         self._ws_bound = 0
+        self._ws_shared = False
 
     def __del__(self):
         try:
@@ -143,8 +144,11 @@ class NativeVGG:
     def ensure_workspace(self, sizes):
         """Bind a torch-owned workspace large enough for every (h, w) in sizes.  Returns True if (re)bound."""
         need = max(self.workspace_bytes(h, w) for h, w in sizes)
-        if self._ws is not None and need <= self._ws_bound:   # compare with what the context was actually given
+        if (self._ws is not None or self._ws_shared) and need <= self._ws_bound:   # what the context was actually given
             return False
+        if self._ws_shared:
+            raise _lib.NativeError('the library-owned (peer-mapped) workspace of this tiled run is too small: '
+                                   f'{need} > {self._ws_bound} bytes')
         self._ws = None
         torch.cuda.empty_cache()  # hand the old block back before asking for the bigger one
         self._ws = torch.empty(need + 2048, dtype=torch.uint8, device=self.device)
@@ -157,6 +161,31 @@ class NativeVGG:
     def release_workspace(self):
         self._ws = None
         self._ws_bound = 0
+
+    def alloc_shared_workspace(self, sizes):
+        """Per-layer-halo mode of a tiled run: the workspace is allocated (cudaMalloc), zeroed and bound by the library so
+        that the neighbouring ranks can map it; returns (64-byte CUDA IPC handle, device pointer)."""
+        need = max(self.workspace_bytes(h, w) for h, w in sizes) + 4096
+        handle = ctypes.create_string_buffer(64)
+        p = ctypes.c_void_p()
+        self._ws = None
+        torch.cuda.empty_cache()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.stb_comm_alloc_workspace(self.ctx, need, handle, ctypes.byref(p), _lib.cur_stream()))
+        self._ws_bound, self._ws_shared = need, True
+        return handle.raw, p.value
+
+    def connect_shared_workspaces(self, items, ipc):
+        if ipc:
+            _lib.check(self.lib.stb_comm_connect_ws_ipc(self.ctx, b''.join(items)))
+        else:
+            arr = (ctypes.c_void_p * len(items))(*items)
+            _lib.check(self.lib.stb_comm_connect_ws_local(self.ctx, ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))))
+
+    def release_shared_workspace(self, unmap_only):
+        _lib.check(self.lib.stb_comm_release_workspace(self.ctx, int(unmap_only)))
+        if not unmap_only:
+            self._ws_bound, self._ws_shared = 0, False
 
     # ------------------------------------------------------------------ target extraction
     def _check_image(self, image):
@@ -328,7 +357,11 @@ class StyleTransfer:
         self._rank = self._group.rank if self._dist else 0
         self._world = self._group.world if self._dist else 1
         self._comm_mode = os.environ.get('STB_COMM', 'peer')   # 'peer': exchanges inside the library; 'nccl': host-driven
+        # 'halo': a band computes its own rows only and pulls one boundary row per layer from its neighbours (their
+        # workspaces are mapped); 'apron': it recomputes 80-row aprons instead (no per-layer exchange)
+        self._tile_mode = os.environ.get('STB_TILE', 'halo')
         self._comm_cap = None
+        self._shared_cap = 0
         self._band = None
 
     # ------------------------------------------------------------------ results
@@ -403,9 +436,10 @@ class StyleTransfer:
             D.exchange_halo(self.image, band)               # refresh the halo rows of the iterate
         self.average.note_update()
 
-    def _setup_comm(self, band, w, cap_h, cap_w):
-        """Per tiled scale (collective over the ranks): make sure the mailboxes exist and are mapped by the peers, zero
-        the iteration stamps between two barriers, hand the band geometry to the library."""
+    def _ensure_peer_memory(self, ws_sizes, cap_h, cap_w):
+        """Collective over the ranks, before the first tiled scale touches the workspace: the mailboxes (bands up to
+        cap_h x cap_w) and, in halo mode, the library-owned workspace (every (h, w) of ws_sizes fits) exist and are
+        mapped by the peers."""
         g, m = self._group, self.model
         if self._comm_mode == 'peer' and (self._comm_cap is None or self._comm_cap[0] < cap_h or self._comm_cap[1] < cap_w):
             ok, mine, err = True, None, None
@@ -437,6 +471,44 @@ class StyleTransfer:
                 warnings.warn(f'peer-memory exchange unavailable on some rank ({err}); falling back to host-driven '
                               'NCCL exchanges')
                 self._comm_mode = 'nccl'
+        if self._comm_mode != 'peer' or self._tile_mode != 'halo':
+            return
+        need = max(m.workspace_bytes(h, w) for h, w in ws_sizes) + 4096
+        grow = need > self._shared_cap
+        if any(g.all_gather_object(grow)):      # all ranks re-create together (a neighbour may map what is freed)
+            ok, mine, err = True, None, None
+            try:
+                if self._shared_cap:
+                    m.release_shared_workspace(unmap_only=True)
+                g.barrier()
+                if self._shared_cap:
+                    m.release_shared_workspace(unmap_only=False)
+                handle, pointer = m.alloc_shared_workspace(ws_sizes)
+                mine = handle if g.peer_kind == 'ipc' else pointer
+            except _lib.NativeError as e:
+                ok, err = False, e
+            infos = g.all_gather_object((ok, mine))
+            if all(i[0] for i in infos):
+                try:
+                    m.connect_shared_workspaces([i[1] for i in infos], g.peer_kind == 'ipc')
+                except _lib.NativeError as e:
+                    ok, err = False, e
+            else:
+                ok = False
+            if all(g.all_gather_object(ok)):
+                self._shared_cap = max(need, m._ws_bound)
+            else:
+                warnings.warn(f'peer-mapped workspace unavailable on some rank ({err}); tiling with recomputed aprons')
+                self._tile_mode = 'apron'
+                self._shared_cap = 0
+                if m._ws_shared:
+                    g.barrier()
+                    m.release_shared_workspace(unmap_only=False)
+
+    def _setup_comm(self, band, w):
+        """Per tiled scale (collective): zero the iteration stamps between two barriers, hand the band geometry to the
+        library."""
+        g, m = self._group, self.model
         if self._comm_mode != 'peer':
             return
         bands = D.all_bands(band.H, self._world)
@@ -562,6 +634,20 @@ class StyleTransfer:
                 for sw, sh, _ in styles:   # a tiled style image needs room for its band only
                     sb = D.make_band(sh, self._rank, self._world) if self._dist else None
                     style_sizes.append((sb.h_local if sb is not None else sh, sw))
+                if band is not None:
+                    # mailboxes / peer-mapped workspace are sized once, for the largest scale of this call (the last)
+                    ew, eh = size_to_fit(content_image.size, scales[-1], scale_up=True)
+                    eb = D.make_band(eh, self._rank, self._world)
+                    cap_h = max(b.h_local for b in D.all_bands(eh, self._world))
+                    end_sizes = [(eb.h_local if eb is not None else eh, ew)]
+                    for simg in style_images:   # style sizes of the last scale (they grow with the scale)
+                        if style_size is None:
+                            lw, lh = size_to_fit(simg.size, round(scales[-1] * style_scale_fac))
+                        else:
+                            lw, lh = size_to_fit(simg.size, style_size)
+                        lb = D.make_band(lh, self._rank, self._world)
+                        end_sizes.append((lb.h_local if lb is not None else lh, lw))
+                    self._ensure_peer_memory([(h_loc, cw)] + style_sizes + end_sizes, max(cap_h, h_loc), max(ew, cw))
                 self.model.ensure_workspace([(h_loc, cw)] + style_sizes)
 
                 self.image = self.model.resize(self.image, (ch, cw), 'bicubic', 'clamp')          # ST:420
@@ -590,10 +676,7 @@ class StyleTransfer:
                 self.model.set_targets(h_loc, cw, content_target, per_content_weight, means, srms, self.style_weights,
                                        tv_weight)
                 if band is not None:
-                    # mailboxes are sized once for the largest scale of this call (the last one)
-                    ew, eh = size_to_fit(content_image.size, scales[-1], scale_up=True)
-                    cap_h = max(b.h_local for b in D.all_bands(eh, self._world))
-                    self._setup_comm(band, cw, max(cap_h, h_loc), max(ew, cw))
+                    self._setup_comm(band, cw)
                     self._band = band
 
                 if optimizer == 'adam':
