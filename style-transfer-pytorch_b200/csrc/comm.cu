@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(256) stats_allreduce_kernel(CommDev c, float* 
 // publish my progress stamp (everything before it on this stream is done: kernel boundary + system fence), wait for the
 // neighbours' same stamp, copy.  Few small CTAs: a waiting rank leaves the GPU to whoever shares it.
 __global__ void __launch_bounds__(256) halo_rows_kernel(CommDev c, HaloRowArgs a) {
+  // launched with programmatic stream serialization: the grid may become resident while the producing kernel drains;
+  // nothing of it is touched (and nothing is published) before that kernel has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   unsigned long long* own = reinterpret_cast<unsigned long long*>(c.mbox[c.rank]);
   const unsigned long long want = own[COMM_ITER] * 256ull + (unsigned long long)a.seq;
   if (threadIdx.x == 0) {
@@ -301,8 +305,16 @@ int launch_halo_rows(const CommDev& c, const HaloRowArgs& a, cudaStream_t s) {
   if (a.src_up == nullptr && a.src_dn == nullptr) return STB_OK;
   long blocks = (long)(a.row_bytes / 16) * 2 / 256 + 1;
   if (blocks > 16) blocks = 16;
-  halo_rows_kernel<<<(int)blocks, 256, 0, s>>>(c, a);
-  STB_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, halo_rows_kernel, c, a));
   return STB_OK;
 }
 
