@@ -37,9 +37,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Waits are bounded: a TMA that faults (or a pipeline bug) must surface as a failed launch (`__trap` -> the next CUDA
+// call of the context returns an error -> STB_ERR_CUDA), not as a stream that never finishes.  mbarrier.try_wait
+// suspends the thread in hardware for a while per call, so the clock is sampled only every 2^14 unsuccessful tries;
+// the bound is ~10 s of SM clock, far beyond any legitimate wait here.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFFu) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > (20ll << 30)) __trap();
+    }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- proxies / fences

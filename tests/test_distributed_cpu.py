@@ -120,3 +120,49 @@ def test_band_geometry():
             assert b.own0 % 16 == 0 and b.top_apron in (0, D.APRON) and b.bottom_apron in (0, D.APRON)
     assert D.make_band(128, 0, 2) is None      # too small to tile: replicated mode
     assert D.make_band(2048, 0, 1) is None
+
+
+def test_thread_group_collectives():
+    """ThreadGroup (the ranks as threads of one process -- how tests/test_gpu_tiled.py runs the tiled path on ONE GPU)
+    offers the same per-scale collectives as TorchGroup: all-reduce, all-gather, broadcast, object gather, row gather."""
+    import threading
+    world, H, W = 3, 400, 8
+    shared = D.ThreadGroup.Shared(world)
+    full = torch.arange(H * W, dtype=torch.float32).reshape(1, 1, H, W)
+    out, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            g = D.ThreadGroup(shared, rank)
+            band = D.make_band(H, rank, world)
+            t = torch.full((4,), float(rank + 1))
+            g.all_reduce_sum(t)
+            objs = g.all_gather_object(('r', rank))
+            b = torch.full((2,), float(rank))
+            g.broadcast(b, 1)
+            local = D.local_slice(full, band).clone()
+            local[:, :, :band.own0] = -1                      # aprons hold garbage: only own rows may be gathered
+            local[:, :, band.own0 + band.own_rows:] = -1
+            out[rank] = (t, objs, b, D.gather_rows(local, band, g))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+            shared.bar.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors, errors
+    for rank in range(world):
+        t, objs, b, gathered = out[rank]
+        assert torch.equal(t, torch.full((4,), 6.0))
+        assert objs == [('r', 0), ('r', 1), ('r', 2)]
+        assert torch.equal(b, torch.full((2,), 1.0))
+        assert torch.equal(gathered, full)
+
+
+def test_tap_pixel_counts_and_all_bands():
+    assert D.tap_pixel_counts(181, 136) == [181 * 136, 90 * 68, 45 * 34, 22 * 17, 11 * 8]
+    bands = D.all_bands(2048, 8)
+    assert [b.own_rows for b in bands] == [256] * 8 and bands[0].top_apron == 0 and bands[3].h_local == 256 + 160
