@@ -415,7 +415,7 @@ def run_native(args, rank, local_rank, world):
         if tiled:
             par = (f'{world}-way spatial tiling: bands of {band.own_rows}+{band.top_apron + band.bottom_apron} halo rows '
                    f'(rank 0); exchanges = ' +
-                   ((f'peer-memory kernels inside the iteration graph, tile mode {st._tile_mode} '
+                   ((f'peer-memory kernels inside the iteration graph, tile mode {"halo" if st._halo_now else "apron"} '
                      '(halo: own rows only + one boundary-row pull per layer; apron: 80 recomputed rows per side) '
                      '+ stats all-reduce, Adam on own rows, image halo pull; CUDA IPC over NVLink')
                     if st._comm_mode == 'peer' else

@@ -141,15 +141,16 @@ STB_API int stb_comm_disconnect(stb_ctx* ctx);  /* unmap the peers' mailboxes (h
  * above / below them from the neighbours' workspaces, which therefore are cudaMalloc blocks of the library mapped by
  * the neighbours (CUDA IPC).  stb_comm_alloc_workspace allocates, zeroes and binds (as stb_bind_workspace does) and
  * returns the 64-byte IPC handle / the pointer; stb_comm_connect_ws_* takes every rank's handle (world x 64 bytes) or
- * pointer in rank order and switches stb_iterate_banded to that mode; stb_comm_release_workspace(unmap_only = 1) unmaps
- * the neighbours, (0) also frees the own block (host barrier in between).  Without these calls a tiled iteration
- * recomputes 80-row aprons instead (no per-layer exchange). */
+ * pointer in rank order; stb_comm_set_geometry(..., halo_rows = 1) then selects that mode for a scale (0: the band
+ * recomputes 80-row aprons instead, no per-layer exchange -- cheaper when the layers are small);
+ * stb_comm_release_workspace(unmap_only = 1) unmaps the neighbours, (0) also frees the own block (host barrier in
+ * between). */
 STB_API int stb_comm_alloc_workspace(stb_ctx* ctx, size_t bytes, void* ipc_handle_out64, void** ptr_out, void* stream);
 STB_API int stb_comm_connect_ws_ipc(stb_ctx* ctx, const void* handles);
 STB_API int stb_comm_connect_ws_local(stb_ctx* ctx, void* const* pointers);
 STB_API int stb_comm_release_workspace(stb_ctx* ctx, int unmap_only);
 STB_API int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_rows, int up_h_local,
-                                  int up_apron_row0, int dn_h_local);
+                                  int up_apron_row0, int dn_h_local, int halo_rows);
 STB_API int stb_comm_reset(stb_ctx* ctx, void* stream);
 STB_API int stb_iterate_banded(stb_ctx* ctx, float* img, float* exp_avg, float* exp_avg_sq, float* ema, int64_t step,
                                float lr, float beta1, float beta2, float adam_eps, float ema_decay,

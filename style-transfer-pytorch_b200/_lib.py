@@ -57,7 +57,7 @@ def _declare(lib):
         'stb_comm_connect_ws_ipc': [vp, vp],
         'stb_comm_connect_ws_local': [vp, pp],
         'stb_comm_release_workspace': [vp, i],
-        'stb_comm_set_geometry': [vp, i, i, i, i, i, i, i],
+        'stb_comm_set_geometry': [vp, i, i, i, i, i, i, i, i],
         'stb_comm_reset': [vp, vp],
         'stb_iterate_banded': [vp, vp, vp, vp, vp, i64, f, f, f, f, f, vp, vp],
         'stb_graph_status': [vp, C.c_char_p, sz],

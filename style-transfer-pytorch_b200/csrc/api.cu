@@ -1094,7 +1094,6 @@ static int connect_ws(stb_ctx* ctx, const void* handles, void* const* pointers) 
     ctx->comm.ws[r] = static_cast<uint8_t*>(p);
   }
   ctx->shared_ws_ipc = handles != nullptr;
-  ctx->halo_mode = true;
   ctx->reset_graphs();
   return STB_OK;
 }
@@ -1142,7 +1141,7 @@ int stb_comm_disconnect(stb_ctx* ctx) {
 
 // geometry of this band and of its neighbours for the current scale (rows in LOCAL coordinates of each rank)
 int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_rows, int up_h_local,
-                          int up_apron_row0, int dn_h_local) {
+                          int up_apron_row0, int dn_h_local, int halo_rows) {
   STB_ENTER(ctx);
   STB_CHECK(ctx->comm_mailbox, STB_ERR_STATE, "stb_comm_create first");
   STB_CHECK(h_local <= ctx->comm_max_h && W <= ctx->comm_max_w && up_h_local <= ctx->comm_max_h &&
@@ -1155,6 +1154,10 @@ int stb_comm_set_geometry(stb_ctx* ctx, int W, int h_local, int own0, int own_ro
   if (has_up) STB_CHECK(up_apron_row0 + COMM_APRON == up_h_local, STB_ERR_INVALID, "upper neighbour geometry");
   ctx->comm.W = W; ctx->comm.h_local = h_local; ctx->comm.own0 = own0; ctx->comm.own_rows = own_rows;
   ctx->comm.up_h_local = up_h_local; ctx->comm.up_apron_row0 = up_apron_row0; ctx->comm.dn_h_local = dn_h_local;
+  // halo_rows = 1: own rows only + one boundary-row pull per layer (needs the peer-mapped workspace); 0: recomputed aprons
+  STB_CHECK(!halo_rows || ctx->comm.ws[ctx->comm.rank] != nullptr, STB_ERR_STATE,
+            "halo-row mode needs stb_comm_alloc_workspace + stb_comm_connect_ws_*");
+  ctx->halo_mode = halo_rows != 0;
   ctx->comm_geometry = true;
   ctx->gslot[3].reset();
   return STB_OK;

@@ -255,10 +255,10 @@ class NativeVGG:
     def comm_disconnect(self):
         _lib.check(self.lib.stb_comm_disconnect(self.ctx))
 
-    def comm_set_geometry(self, w, band, up, down):
+    def comm_set_geometry(self, w, band, up, down, halo_rows):
         _lib.check(self.lib.stb_comm_set_geometry(self.ctx, w, band.h_local, band.own0, band.own_rows,
                                                   up.h_local if up else 0, up.own0 + up.own_rows if up else 0,
-                                                  down.h_local if down else 0))
+                                                  down.h_local if down else 0, int(halo_rows)))
 
     def comm_reset(self):
         _lib.check(self.lib.stb_comm_reset(self.ctx, _lib.cur_stream()))
@@ -358,8 +358,12 @@ class StyleTransfer:
         self._world = self._group.world if self._dist else 1
         self._comm_mode = os.environ.get('STB_COMM', 'peer')   # 'peer': exchanges inside the library; 'nccl': host-driven
         # 'halo': a band computes its own rows only and pulls one boundary row per layer from its neighbours (their
-        # workspaces are mapped); 'apron': it recomputes 80-row aprons instead (no per-layer exchange)
-        self._tile_mode = os.environ.get('STB_TILE', 'halo')
+        # workspaces are mapped); 'apron': it recomputes 80-row aprons instead (no per-layer exchange); 'auto' (default):
+        # per scale, halo rows when the image is at least HALO_MIN_WIDTH wide.  Measured: the ~28
+        # exchanges of an iteration cost ~0.36 ms whatever the size, the aprons 160 rows x W of convolution work
+        # (~1.7e-4 ms per pixel of width): 0.34 ms at W = 2048 (aprons win), 0.69 ms at W = 4096 (halo rows win).
+        self._tile_mode = os.environ.get('STB_TILE', 'auto')
+        self._halo_now = False
         self._comm_cap = None
         self._shared_cap = 0
         self._band = None
@@ -471,7 +475,7 @@ class StyleTransfer:
                 warnings.warn(f'peer-memory exchange unavailable on some rank ({err}); falling back to host-driven '
                               'NCCL exchanges')
                 self._comm_mode = 'nccl'
-        if self._comm_mode != 'peer' or self._tile_mode != 'halo':
+        if self._comm_mode != 'peer' or self._tile_mode == 'apron' or not self._wants_halo(cap_w):
             return
         need = max(m.workspace_bytes(h, w) for h, w in ws_sizes) + 4096
         grow = need > self._shared_cap
@@ -505,6 +509,11 @@ class StyleTransfer:
                     g.barrier()
                     m.release_shared_workspace(unmap_only=False)
 
+    HALO_MIN_WIDTH = 2400
+
+    def _wants_halo(self, w):
+        return self._tile_mode == 'halo' or (self._tile_mode == 'auto' and w >= self.HALO_MIN_WIDTH)
+
     def _setup_comm(self, band, w):
         """Per tiled scale (collective): zero the iteration stamps between two barriers, hand the band geometry to the
         library."""
@@ -517,7 +526,8 @@ class StyleTransfer:
         g.barrier()
         up = bands[self._rank - 1] if self._rank > 0 else None
         down = bands[self._rank + 1] if self._rank + 1 < self._world else None
-        m.comm_set_geometry(w, band, up, down)
+        self._halo_now = bool(self._wants_halo(w) and m._ws_shared and self._shared_cap)
+        m.comm_set_geometry(w, band, up, down, self._halo_now)
 
     def _style_stats(self, simg, sh, sw):
         """(means, second raw moments) of one style image (ST:440-443).  Under torch.distributed a large style image

@@ -37,7 +37,7 @@ def run_tiled(world, content, style, wts, kw):
             with contextlib.redirect_stdout(io.StringIO()):
                 img = st.stylize(content, [style], callback=lambda it: trace.append(it.loss), **kw)
             results[rank] = (np.array(trace), np.asarray(img, dtype=np.float32),
-                             (st._comm_mode, st._tile_mode), st.model.graph_status())
+                             (st._comm_mode, 'halo' if st._halo_now else 'apron'), st.model.graph_status())
         except BaseException as e:  # noqa: BLE001 -- report and release the other ranks
             errors.append((rank, repr(e)))
             shared.bar.abort()
@@ -61,18 +61,25 @@ def run_single(content, style, wts, kw):
     return np.array(trace), np.asarray(img, dtype=np.float32)
 
 
+TILE = os.environ.get('STB_TILE', 'auto')
+
+
+@pytest.mark.parametrize('tile', ['halo', 'apron'])
 @pytest.mark.parametrize('world,W,H,its', [(2, 512, 384, 6), (3, 200, 400, 5), (2, 362, 384, 4), (4, 256, 512, 4)])
-def test_tiled_threads_equal_single_gpu(vgg_weights, world, W, H, its):
+def test_tiled_threads_equal_single_gpu(vgg_weights, monkeypatch, tile, world, W, H, its):
     """Loss trace and result of the banded run (world ranks) vs the untiled run of the same job.  362 is not a multiple
     of 4 (scalar row kernels); 3 ranks give unequal bands; 4 ranks have two interior bands with aprons on both sides."""
+    monkeypatch.setenv('STB_TILE', tile)
+    global TILE
+    TILE = tile
     content, style = O.synth_image(1, 16, W, H), O.synth_image(2, 32, W // 2 + 40, H // 2 + 24)
     scale = max(H, W)
     kw = dict(min_scale=scale, end_scale=scale, initial_iterations=its)
     tiled = run_tiled(world, content, style, vgg_weights, kw)
     tr_s, img_s = run_single(content, style, vgg_weights, kw)
     for rank, (tr, img, mode, (gstat, note)) in enumerate(tiled):
-        # exchanges inside the library; tile mode as requested (default: per-layer halo rows, no recomputed aprons)
-        assert mode == ('peer', os.environ.get('STB_TILE', 'halo'))
+        # exchanges inside the library; tile mode as requested (these images are narrow: 'auto' picks aprons)
+        assert mode == ('peer', {'auto': 'apron'}.get(TILE, TILE))
         assert gstat == 1, f'rank {rank}: iterations did not replay as a CUDA graph ({note})'
         assert len(tr) == its
         rel = np.abs(tr - tr_s) / np.abs(tr_s)
@@ -84,9 +91,11 @@ def test_tiled_threads_equal_single_gpu(vgg_weights, world, W, H, its):
         np.testing.assert_array_equal(img, tiled[0][1])
 
 
-def test_tiled_pyramid_mixes_replicated_and_banded_scales(vgg_weights):
+@pytest.mark.parametrize('tile', ['halo', 'apron'])
+def test_tiled_pyramid_mixes_replicated_and_banded_scales(vgg_weights, monkeypatch, tile):
     """Small scales run replicated (too few rows to tile), the larger ones banded; Adam state and the step counter are
     carried across both kinds of scale (ST:285-295, 460-462), the mailboxes are sized once for the last scale."""
+    monkeypatch.setenv('STB_TILE', tile)
     W, H = 288, 384
     content, style = O.synth_image(1, 16, W, H), O.synth_image(2, 32, 260, 300)
     kw = dict(min_scale=128, end_scale=384, iterations=3, initial_iterations=4)

@@ -43,7 +43,7 @@ def run(distributed):
     with contextlib.redirect_stdout(io.StringIO()):
         img = st.stylize(content, styles, callback=lambda it: trace.append((it.w, it.h, it.i, it.loss, it.time)), **kw)
     torch.cuda.synchronize()
-    return trace, np.asarray(img, dtype=np.float32), time.perf_counter() - t0, st._comm_mode, st.model.graph_status()
+    return trace, np.asarray(img, dtype=np.float32), time.perf_counter() - t0, (st._comm_mode, st._tile_mode, st._halo_now), st.model.graph_status()
 
 
 tr_t, img_t, sec_t, mode, gstat = run(None)

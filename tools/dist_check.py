@@ -40,7 +40,7 @@ def run(distributed):
     with contextlib.redirect_stdout(io.StringIO()):
         img = st.stylize(content, [style], callback=lambda it: tr.append(it.loss), **kw)
     torch.cuda.synchronize()
-    MODES.append(((st._comm_mode, st._tile_mode) if distributed is not False else 'single', st.model.graph_status()))
+    MODES.append(((st._comm_mode, 'halo' if st._halo_now else 'apron') if distributed is not False else 'single', st.model.graph_status()))
     return np.array(tr), np.asarray(img, dtype=np.float32), time.perf_counter() - t0
 
 
