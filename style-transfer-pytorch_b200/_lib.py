@@ -6,8 +6,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / 'libstb200.so'
+LIB_PATH = Path(os.environ.get('STB_LIB', PKG_DIR / 'libstb200.so'))   # STB_LIB: A/B a differently built library
 TEST_LIB_PATH = PKG_DIR / 'libstb200_test.so'
 
 STB_ERR_INVALID = -1

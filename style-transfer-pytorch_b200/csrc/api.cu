@@ -1019,6 +1019,7 @@ int stb_comm_connect_ipc(stb_ctx* ctx, const void* handles) {
   }
   ctx->comm_ipc = true;
   ctx->comm_ready = true;
+  ctx->comm.pdl = 1;   // one process per GPU
   return STB_OK;
 }
 
@@ -1043,6 +1044,7 @@ int stb_comm_connect_local(stb_ctx* ctx, void* const* mailboxes) {
     ctx->comm.mbox[r] = static_cast<uint8_t*>(mailboxes[r]);
   }
   ctx->comm_ready = true;
+  ctx->comm.pdl = 0;   // ranks may share a device (see CommDev::pdl)
   return STB_OK;
 }
 

@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) halo_rows_kernel(CommDev c, HaloRowArgs a
   // launched with programmatic stream serialization: the grid may become resident while the producing kernel drains;
   // nothing of it is touched (and nothing is published) before that kernel has completed
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // letting the NEXT kernel (a PDL-launched conv) become resident now is only safe when this rank has the GPU to itself:
+  // its CTAs would sit on every SM waiting for this kernel, which waits for a rank that may need those SMs (CommDev::pdl)
+  if (c.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   unsigned long long* own = reinterpret_cast<unsigned long long*>(c.mbox[c.rank]);
   const unsigned long long want = own[COMM_ITER] * 256ull + (unsigned long long)a.seq;
   if (threadIdx.x == 0) {
@@ -313,7 +315,7 @@ int launch_halo_rows(const CommDev& c, const HaloRowArgs& a, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = c.pdl ? 1 : 0;
   STB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, halo_rows_kernel, c, a));
   return STB_OK;
 }

@@ -153,6 +153,9 @@ struct CommDev {  // passed by value to the exchange kernels
   int up_h_local, up_apron_row0, dn_h_local;  // neighbours' local heights; first bottom-apron row of the upper band
   uint8_t* ws[COMM_MAX_RANKS];                // per-layer-halo mode: every rank's WORKSPACE as mapped here (else null)
   unsigned long long timeout_ns;              // a peer wait longer than this traps instead of hanging
+  int pdl;  // 1: exchange kernels may launch their successor early (programmatic dependent launch).  Only when every
+            // rank has its own GPU: with several ranks on ONE device (test emulation) an early-resident conv grid that
+            // waits for an exchange kernel, which waits for another rank, would starve that rank of SMs.
 };
 size_t comm_mailbox_bytes(size_t stats_floats, int max_h_local, int max_W, size_t off[5]);
 int launch_comm_phase(const CommDev& c, int phase, cudaStream_t s);   // 0 begin, 1 stats, 2 grad, 3 end

@@ -53,8 +53,13 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef STB_MBAR_UNBOUNDED
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity);
+#endif
 }
 
 // ---------------------------------------------------------------- proxies / fences
