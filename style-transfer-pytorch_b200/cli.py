@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import os
 import sys
 from dataclasses import asdict
 from pathlib import Path
@@ -69,7 +70,16 @@ def main(argv=None):
     content = _read_rgb(args.content)
     styles = [_read_rgb(p) for p in args.styles]
 
+    # one process per GPU under torchrun: the ranks tile the large scales between them (distributed.py); rank 0 talks
+    # and writes, every rank takes part in the collective gathers behind get_image()
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', 1), ('RANK', 0), ('LOCAL_RANK', 0)))
     devices = [torch.device(d) for d in args.devices]
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        devices = [torch.device('cuda', local)]
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=devices[0])
     if not devices:
         if not torch.cuda.is_available():
             sys.exit('no CUDA device: this build has no CPU path')
@@ -95,10 +105,14 @@ def main(argv=None):
 
     def on_iterate(it):
         trace.append(asdict(it))
-        print(f'Size: {it.w}x{it.h}, iteration: {it.i}, loss: {it.loss:g}')
+        if rank == 0:
+            print(f'Size: {it.w}x{it.h}, iteration: {it.i}, loss: {it.loss:g}')
         last_of_scale = it.i == it.i_max
         if (args.save_every and it.i % args.save_every == 0) or (last_of_scale and max(it.w, it.h) != args.end_scale):
-            writer.submit_snapshot(st, out_path)
+            if rank == 0:
+                writer.submit_snapshot(st, out_path)
+            else:
+                st.get_image_tensor()   # the gather of a tiled scale is collective
 
     kwargs = {k: getattr(args, k) for k in _SHORT}
     try:
@@ -107,6 +121,8 @@ def main(argv=None):
         pass
     writer.close()
     image = st.get_image()
+    if rank != 0:
+        return
     if image is not None:
         print(f'Writing image to {out_path}.')
         image.save(out_path)

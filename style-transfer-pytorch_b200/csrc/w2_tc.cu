@@ -76,12 +76,6 @@ __device__ __forceinline__ void split_tf32(float v, float& h, float& l) {
   h = rna_tf32(v);
   l = rna_tf32(v - h);
 }
-__device__ __forceinline__ void store_split4(float* hi_ptr, float* lo_ptr, float4 v) {
-  float4 h, l;
-  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<float4*>(hi_ptr) = h;
-  *reinterpret_cast<float4*>(lo_ptr) = l;
-}
 __device__ __forceinline__ void store_split(float* m, size_t nn, size_t e, float v) {
   float h, l;
   split_tf32(v, h, l);
