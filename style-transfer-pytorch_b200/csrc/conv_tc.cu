@@ -189,8 +189,8 @@ pixel_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             if (leader) {
               const uint32_t b_lo = umma_desc_lo(b_base0 + sb * C::B_STAGE_BYTES);
-              // k outer, sub-tile inner: two consecutive MMAs never accumulate into the same TMEM tile (a dependent
-              // tcgen05.mma waits for its predecessor's accumulator; STB_MMA_ORDER=0 restores sub-tile-major order)
+              // experiment (STB_MMA_ORDER=1): k outer, sub-tile inner, so that two consecutive MMAs never accumulate into
+              // the same TMEM tile.  Measured slower than the default order below.
               if (p.mma_interleave) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -458,7 +458,10 @@ int launch_pixel_gemm(const PixelGemmArgs& a, cudaStream_t stream) {
   kp.a2_row0 = a.a2_row0;
   kp.bias = a.bias; kp.mask_src = a.mask_src; kp.ctarget = a.ctarget; kp.cscale = a.cscale;
   kp.row_lo = a.row_lo; kp.row_hi = a.row_hi;
-  static const int mma_order = [] { const char* e = getenv("STB_MMA_ORDER"); return (e && e[0] == '0') ? 0 : 1; }();
+  // default: sub-tile-major (four k-steps of one sub-tile back to back).  The k-major order (STB_MMA_ORDER=1) was tried
+  // against the hypothesis that dependent accumulations stall the pipe: under ncu it is 8-17 % SLOWER on the N <= 128
+  // launches (alternating A descriptors), see DESIGN.md section 4.1.
+  static const int mma_order = [] { const char* e = getenv("STB_MMA_ORDER"); return (e && e[0] == '1') ? 1 : 0; }();
   kp.mma_interleave = mma_order;
   STB_CHECK(a.mode >= 0 && a.mode <= 2, STB_ERR_INVALID, "pixel_gemm: mode=%d", a.mode);
   if (a.mode == 1) STB_CHECK(a.mask_src != nullptr, STB_ERR_INVALID, "pixel_gemm: bwd needs mask_src");

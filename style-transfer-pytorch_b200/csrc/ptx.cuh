@@ -37,10 +37,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Waits are bounded: a TMA that faults (or a pipeline bug) must surface as a failed launch (`__trap` -> the next CUDA
-// call of the context returns an error -> STB_ERR_CUDA), not as a stream that never finishes.  mbarrier.try_wait
-// suspends the thread in hardware for a while per call, so the clock is sampled only every 2^14 unsuccessful tries;
-// the bound is ~10 s of SM clock, far beyond any legitimate wait here.
+// Plain spin on mbarrier.try_wait (which suspends the thread in hardware between tries).  A bounded variant -- sample the
+// clock every 2^14 tries, `__trap` after ~10 s so that a faulted TMA surfaces as a failed launch instead of a stream that
+// never finishes -- is available with -DSTB_MBAR_BOUNDED for debugging; it is NOT the default because the extra branch /
+// out-of-line call in the tcgen05 issue loops cost 12-20 % on the narrow (N <= 128) convolutions, whose MMAs are short
+// enough to be issue-rate sensitive (measured: <64,0> 332 -> 401 us).  The cross-CTA waits that can really dead-lock
+// (peer stamps, the W2 grid barrier) have their own timeouts.
+#ifdef STB_MBAR_BOUNDED
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
@@ -53,14 +56,15 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef STB_MBAR_UNBOUNDED
-  while (!mbar_try_wait(bar, parity)) {
-  }
-#else
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity);
-#endif
 }
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+#endif
 
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
