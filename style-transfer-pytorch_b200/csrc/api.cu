@@ -233,7 +233,7 @@ int level_of(int conv) {
 }
 // tensor with C channels at pyramid level `level` (width w_l); off_* = its byte offset in the plan of me / up / down.
 // sync_only: publish + wait the stamps without copying (a buffer the neighbours pulled from is about to be rewritten).
-int halo_exchange(stb_ctx* ctx, const Plan& pl, int level, int w_l, int C, size_t off_me, size_t off_up, size_t off_dn,
+int halo_exchange(stb_ctx* ctx, int level, int w_l, int C, size_t off_me, size_t off_up, size_t off_dn,
                   bool sync_only, cudaStream_t s) {
   const CommDev& c = ctx->comm;
   const bool has_up = c.rank > 0, has_dn = c.rank + 1 < c.world;
@@ -255,7 +255,6 @@ int halo_exchange(stb_ctx* ctx, const Plan& pl, int level, int w_l, int C, size_
     a.src_dn = c.ws[c.rank + 1] + off_dn + (size_t)(COMM_APRON >> level) * row_bytes;
     a.dst_dn = ctx->ws + off_me + (size_t)(o0 + r) * row_bytes;
   }
-  (void)pl;
   return launch_halo_rows(c, a, s);
 }
 
@@ -297,7 +296,7 @@ int forward(stb_ctx* ctx, const Plan& pl, const float* img, int last_conv, bool 
     ctx->prof.begin(PC_CONV_FWD, s);
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
-    if (halo && i < last_conv) STB_TRY(halo_exchange(ctx, pl, x_level, x_w, kCout[i], x_me, x_up, x_dn, false, s));
+    if (halo && i < last_conv) STB_TRY(halo_exchange(ctx, x_level, x_w, kCout[i], x_me, x_up, x_dn, false, s));
   }
   return STB_OK;
 }
@@ -681,7 +680,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
     STB_TRY(launch_pixel_gemm(a, s));
     ctx->prof.end(s);
     if (halo)
-      STB_TRY(halo_exchange(ctx, pl, level_of(12), pl.w[12], 512, pl.g_off[cur], halo->up.g_off[cur], halo->dn.g_off[cur],
+      STB_TRY(halo_exchange(ctx, level_of(12), pl.w[12], 512, pl.g_off[cur], halo->up.g_off[cur], halo->dn.g_off[cur],
                             false, s));
   }
   for (int i = NCONV - 1; i >= 1; --i) {
@@ -703,7 +702,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
                                 pl.w[i - 1], kCout[i - 1], s));
       } else {
         // g[cur ^ 1] is the buffer the neighbours pulled their halo rows from one exchange ago: make sure they are done
-        STB_TRY(halo_exchange(ctx, pl, level_of(i), pl.w[i], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
+        STB_TRY(halo_exchange(ctx, level_of(i), pl.w[i], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
                               halo->dn.g_off[cur], true, s));
         const BandRows bp = band_rows(ctx, pl, i - 1);   // own rows before the pool
         const int C = kCout[i - 1];
@@ -714,7 +713,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
       ctx->prof.end(s);
       cur ^= 1;
       if (halo)
-        STB_TRY(halo_exchange(ctx, pl, level_of(i - 1), pl.w[i - 1], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
+        STB_TRY(halo_exchange(ctx, level_of(i - 1), pl.w[i - 1], kCout[i - 1], pl.g_off[cur], halo->up.g_off[cur],
                               halo->dn.g_off[cur], false, s));
     } else {
       a.mode = 1;
@@ -738,7 +737,7 @@ int iterate_bwd(stb_ctx* ctx, const Plan& pl, float* img, float* exp_avg, float*
       ctx->prof.end(s);
       cur ^= 1;
       if (halo)
-        STB_TRY(halo_exchange(ctx, pl, level_of(i - 1), pl.w[i - 1], kCin[i], pl.g_off[cur], halo->up.g_off[cur],
+        STB_TRY(halo_exchange(ctx, level_of(i - 1), pl.w[i - 1], kCin[i], pl.g_off[cur], halo->up.g_off[cur],
                               halo->dn.g_off[cur], false, s));
     }
   }
